@@ -1,0 +1,180 @@
+/*
+ * plb.h -- C ABI of libplb, the B200 (sm_100a) back end of PyLaBolt's fluidLB
+ * time step (D2Q9, fp64).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy
+ * types.  Every entry point replaces a piece of the reference's Python/numba
+ * path (Malyadeep/pylabolt; citations are file:line in that repository):
+ *
+ *   reference seam: Solver.execute_single_time_step, bound in Solver.compile
+ *   (pylabolt/solvers/fluidLB.py:273-280) and called once per step by
+ *   Solver.run (:356).  A "b200" back end rebinds that slot to plb_step().
+ *
+ * Host arrays cross the boundary in the REFERENCE'S OWN LAYOUTS
+ * (pylabolt/base/fields.py:50-92): one ghost ring, flat node index
+ * ind = x * (ny + 2) + y with y contiguous, populations (size, 9), vectors
+ * (size, 2), flags one byte per node.  The library owns all device memory
+ * behind the opaque handle and keeps its own structure-of-arrays layout;
+ * host pointers are borrowed for the duration of a call only.
+ *
+ * Error convention: every function returns PLB_OK (0) or a negative code;
+ * plb_last_error() returns the message of the last failure on this thread.
+ * A handle is driven by one host thread.  plb_step() is asynchronous; it is
+ * ordered before any later plb_download / plb_sync on the same handle.
+ */
+#ifndef PLB_H
+#define PLB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLB_ABI_VERSION 1
+
+enum plb_status {
+    PLB_OK = 0,
+    PLB_ERR_INVALID = -1,   /* bad argument / configuration               */
+    PLB_ERR_CUDA = -2,      /* CUDA runtime failure (message has details) */
+    PLB_ERR_STATE = -3,     /* call made in the wrong state               */
+    PLB_ERR_NCCL = -4,      /* NCCL failure or NCCL not loadable          */
+    PLB_ERR_NOMEM = -5
+};
+
+/* collision_dict.fluid.model, pylabolt/solvers/fluidLB.py:35-40 */
+enum plb_collision { PLB_BGK = 0, PLB_MRT = 1 };
+/* collision_dict.fluid.forcing_model, pylabolt/solvers/fluidLB.py:28-34 */
+enum plb_forcing { PLB_FORCING_NONE = 0, PLB_GUO_LINEAR = 1,
+                   PLB_GUO_SECOND_ORDER = 2 };
+/* boundary_dict.<name>.fluid.type, pylabolt/base/boundary.py:377-382;
+ * zero_gradient is listed by README.rst:83 but has no upstream kernel. */
+enum plb_bc_type { PLB_BC_BOUNCE_BACK = 0, PLB_BC_FIXED_VELOCITY = 1,
+                   PLB_BC_FIXED_PRESSURE = 2, PLB_BC_PERIODIC = 3,
+                   PLB_BC_ZERO_GRADIENT = 4 };
+
+/* Host-side fields that can be uploaded / downloaded.  "padded" = the
+ * reference layout with the ghost ring, (nx+2)*(ny+2) nodes; "inner" = ghost
+ * ring stripped, nx*ny nodes, x-major (what
+ * pylabolt/parallel/cpu/io_operator_kernels.py:5-52 produces for np.savez). */
+enum plb_field {
+    PLB_SOLID = 0,          /* uint8  padded  fields.solid (incl. ghost flags
+                               filled by base/obstacle_operator.py:36-41)  */
+    PLB_DENSITY = 1,        /* double padded  fields.density               */
+    PLB_VELOCITY = 2,       /* double padded (size,2) fields.velocity      */
+    PLB_POP = 3,            /* double padded (size,9) fields.pop_fluid_new */
+    PLB_DENSITY_INNER = 4,  /* double inner                                */
+    PLB_VELOCITY_INNER = 5  /* double inner (n,2)                          */
+};
+
+/* One rank's configuration.  Values are computed by the caller exactly as the
+ * reference computes them and are used verbatim by the kernels. */
+typedef struct plb_config {
+    int32_t abi_version;       /* PLB_ABI_VERSION                                   */
+    int32_t device;            /* CUDA device ordinal                               */
+    int64_t nx, ny;            /* this rank's interior nodes: Domain.Nx_rank/Ny_rank,
+                                  pylabolt/parallel/domain.py:54-76                 */
+    int32_t x_periodic;        /* Boundary.x_periodic, base/boundary.py:553-556     */
+    int32_t y_periodic;        /* Boundary.y_periodic                               */
+    int32_t left_neighbor;     /* 1 if column x=-1 is fed by a neighbour rank or by
+                                  the periodic image (MPIOperator.left_rank is not
+                                  None, parallel/MPI_operator.py:131-136)           */
+    int32_t right_neighbor;    /* same for column x=nx (MPI_operator.py:138-142)    */
+    int32_t collision;         /* enum plb_collision                                */
+    int32_t forcing;           /* enum plb_forcing                                  */
+    double omega;              /* 1/tau, base/collision_operator.py:89-91           */
+    double mrt_rates[9];       /* S, base/collision_operator.py:159-163             */
+    double gravity[2];         /* ForceOperator.gravity, base/force_operator.py:59-79 */
+    double inv_cs_2, inv_cs_4; /* Lattice, base/lattice.py:41-44                    */
+    double float_min;          /* Control.float_min, base/control.py:49             */
+    double weights[9];         /* Lattice.weights, base/lattice.py:54-57            */
+} plb_config;
+
+typedef struct plb_solver *plb_handle;
+
+/* ---- life cycle -------------------------------------------------------- */
+
+/* Allocates the device lattices (two-lattice SoA, fp64) for one rank.
+ * Replaces State.set_backend / Fields.set_backend device mirroring
+ * (pylabolt/base/fields.py:192-227). */
+int plb_create(const plb_config *config, plb_handle *out);
+void plb_destroy(plb_handle h);
+const char *plb_last_error(void);
+
+/* ---- geometry ---------------------------------------------------------- */
+
+/* One boundary element, in boundary_dict order (later elements win shared
+ * links, base/boundary_operator.py:153-157).  Mirrors BoundaryElement
+ * (pylabolt/base/boundary.py:7-127): boundary_nodes are padded flat indices,
+ * out_list / inv_list the three outgoing / incoming directions, normal the
+ * inward surface normal as integers, vector / scalar the fluid value. */
+int plb_add_boundary_element(plb_handle h, int32_t bc_type,
+                             const int64_t *boundary_nodes, int64_t n_nodes,
+                             const int64_t out_list[3],
+                             const int64_t inv_list[3],
+                             const int64_t normal[2],
+                             const double vector_fluid[2],
+                             double scalar_fluid);
+
+/* Classifies every node from the uploaded PLB_SOLID flags and the boundary
+ * elements (bulk / skip / link node), builds the link lists and the slab-face
+ * masks and uploads them.  Must be called once after PLB_SOLID and all
+ * elements are set and before plb_initialize_pop / plb_step. */
+int plb_finalize_geometry(plb_handle h);
+
+/* ---- data -------------------------------------------------------------- */
+
+int plb_upload(plb_handle h, int32_t field, const void *host, size_t bytes);
+int plb_download(plb_handle h, int32_t field, void *host, size_t bytes);
+
+/* f = f_eq(rho, u) on fluid nodes, 0 elsewhere: CollisionOperator.initialize_pop,
+ * pylabolt/parallel/cpu/equilibrium_kernels.py:38-78. */
+int plb_initialize_pop(plb_handle h);
+
+/* ---- the hot path ------------------------------------------------------ */
+
+/* Advances n_steps reference time steps (Solver.single_time_step,
+ * pylabolt/solvers/fluidLB.py:206-253, phases 2-8 fused).  If store_moments
+ * is non-zero the LAST step also stores rho and u (phases 2-4 of that step),
+ * which is what fields.density / fields.velocity hold after the reference
+ * has executed the same number of steps. */
+int plb_step(plb_handle h, int64_t n_steps, int32_t store_moments);
+int plb_sync(plb_handle h);
+
+/* ---- diagnostics ("next" rows) ----------------------------------------- */
+
+/* Residue sums of utils/residues.py:171-222 on the stored moments:
+ * out = {num_rho, den_rho, num_ux, den_ux, num_uy, den_uy}; the library keeps
+ * field_old and updates it, like cpu/compute_residues_kernels.py:6-73. */
+int plb_residue_sums(plb_handle h, double out[6]);
+
+/* ---- multi-GPU (x-slabs, one process per GPU) -------------------------- */
+
+/* 128-byte NCCL unique id, created on one rank and broadcast by the caller
+ * (torch.distributed is only the bootstrap). */
+int plb_comm_unique_id(void *id128);
+/* Joins the slab ring.  left_rank / right_rank are the ranks that own the
+ * neighbouring slabs (-1 = none).  Replaces MPIOperator.find_neighbor_ranks
+ * and halo_exchange, pylabolt/parallel/MPI_operator.py:116-259. */
+int plb_comm_init(plb_handle h, const void *id128, int32_t rank,
+                  int32_t n_ranks, int32_t left_rank, int32_t right_rank);
+
+/* ---- measurement helpers ----------------------------------------------- */
+
+/* CUDA events on the library's own stream (slot 0..7). */
+int plb_event_record(plb_handle h, int32_t slot);
+int plb_event_elapsed_ms(plb_handle h, int32_t start_slot, int32_t stop_slot,
+                         float *ms);
+/* Kernels launched by this handle since creation / since the last reset. */
+int64_t plb_kernel_launches(plb_handle h, int32_t reset);
+/* Pinned host memory for upload / download buffers. */
+int plb_host_alloc(void **ptr, size_t bytes);
+int plb_host_free(void *ptr);
+/* Writes a scratch buffer larger than L2 (bench hygiene). */
+int plb_flush_l2(plb_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLB_H */

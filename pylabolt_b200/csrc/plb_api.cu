@@ -1,0 +1,880 @@
+// plb_api.cu -- host side of libplb: the C ABI of include/plb.h.
+//
+// Owns the device lattices, classifies nodes into bulk / link / solid / ghost
+// from the reference's own flags and boundary elements, builds the link lists
+// and drives the per-step kernel sequence (optionally with a slab-face
+// exchange over NCCL, loaded at run time with dlopen so that a single-GPU
+// process needs no NCCL at all).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include <nccl.h>   // types and prototypes only; symbols come from dlopen
+
+#include "../../include/plb.h"
+#include "plb_internal.h"
+
+using namespace plb;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                        \
+    do {                                                                      \
+        cudaError_t err__ = (expr);                                           \
+        if (err__ != cudaSuccess)                                             \
+            return fail(PLB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,         \
+                        cudaGetErrorString(err__), __FILE__, __LINE__);       \
+    } while (0)
+
+constexpr int CX[Q] = PLB_CX_LIST;
+constexpr int CY[Q] = PLB_CY_LIST;
+constexpr int INV[Q] = PLB_INV_LIST;
+
+// ---- NCCL through dlopen ---------------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl()
+{
+    if (g_nccl.lib) return PLB_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(PLB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                      \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name)); \
+    if (!g_nccl.field) return fail(PLB_ERR_NCCL, "NCCL symbol %s missing", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.lib = lib;
+    return PLB_OK;
+}
+
+#define NCCL_TRY(expr)                                                        \
+    do {                                                                      \
+        ncclResult_t r__ = (expr);                                            \
+        if (r__ != ncclSuccess)                                               \
+            return fail(PLB_ERR_NCCL, "%s failed: %s", #expr,                 \
+                        g_nccl.GetErrorString(r__));                          \
+    } while (0)
+
+struct ElementHost {
+    int32_t type;
+    std::vector<int64_t> nodes;
+    int64_t out[3], inv[3], normal[2];
+    double vector[2], scalar;
+};
+
+}  // namespace
+
+struct plb_solver {
+    plb_config cfg;
+    Layout L;
+    KParams kp;
+    int variant = 1;                 // 0 scalar, 1 vec2 (env PLB_KERNEL)
+
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
+    cudaEvent_t events[8] = {};
+
+    double *f[2] = {nullptr, nullptr};   // two lattices, 9 planes each
+    int cur = 0;
+    double *mom = nullptr;               // rho, ux, uy planes
+    double *mom_old = nullptr;           // residue field_old (lazy)
+    double *res_partials = nullptr, *res_out = nullptr;
+    uint8_t *code = nullptr;
+    double *staging = nullptr;
+    size_t staging_bytes = 0;
+    double *flush_buf = nullptr;
+
+    std::vector<uint8_t> solid_host;
+    std::vector<ElementHost> elements;
+    bool finalized = false;
+
+    ElementDev *elements_dev = nullptr;
+    LinkNode *links_dev = nullptr;
+    int64_t n_links = 0;
+    std::vector<std::pair<ZgLink *, int64_t>> zg_dev;
+    uint8_t *mask_left = nullptr, *mask_right = nullptr;
+    int64_t n_bulk = 0, n_solid = 0;
+
+    ncclComm_t comm = nullptr;
+    int rank = 0, n_ranks = 1, left_rank = -1, right_rank = -1;
+    double *recv_left = nullptr, *recv_right = nullptr;   // 3 * ny each
+
+    int64_t launches = 0;
+    int64_t steps_done = 0;
+
+    double *rho() const { return mom; }
+    double *ux() const { return mom + L.plane; }
+    double *uy() const { return mom + 2 * L.plane; }
+};
+
+namespace {
+
+int ensure_staging(plb_solver *s, size_t bytes)
+{
+    if (s->staging_bytes >= bytes) return PLB_OK;
+    if (s->staging) CUDA_TRY(cudaFree(s->staging));
+    s->staging = nullptr;
+    s->staging_bytes = 0;
+    CUDA_TRY(cudaMalloc(&s->staging, bytes));
+    s->staging_bytes = bytes;
+    return PLB_OK;
+}
+
+constexpr size_t CHUNK_BYTES = size_t(64) << 20;
+
+// reference layout (padded, ncomp interleaved) -> planes
+int upload_padded(plb_solver *s, const double *host, int ncomp, double *planes,
+                  int64_t plane_stride)
+{
+    const Layout &L = s->L;
+    const int64_t row_elems = (L.ny + 2) * ncomp;
+    const int64_t rows_per_chunk =
+        std::max<int64_t>(1, int64_t(CHUNK_BYTES / (row_elems * sizeof(double))));
+    if (int rc = ensure_staging(s, size_t(rows_per_chunk) * row_elems * sizeof(double)))
+        return rc;
+    for (int64_t row0 = 0; row0 < L.nx + 2; row0 += rows_per_chunk) {
+        const int64_t nrows = std::min(rows_per_chunk, L.nx + 2 - row0);
+        CUDA_TRY(cudaMemcpyAsync(s->staging, host + row0 * row_elems,
+                                 size_t(nrows) * row_elems * sizeof(double),
+                                 cudaMemcpyHostToDevice, s->stream));
+        s->launches += launch_unpack_rows(L, s->staging, ncomp, planes,
+                                          plane_stride, row0, nrows, s->stream);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return PLB_OK;
+}
+
+int download_padded(plb_solver *s, double *host, int ncomp, const double *planes,
+                    int64_t plane_stride, int zero_mode)
+{
+    const Layout &L = s->L;
+    const int64_t row_elems = (L.ny + 2) * ncomp;
+    const int64_t rows_per_chunk =
+        std::max<int64_t>(1, int64_t(CHUNK_BYTES / (row_elems * sizeof(double))));
+    if (int rc = ensure_staging(s, size_t(rows_per_chunk) * row_elems * sizeof(double)))
+        return rc;
+    for (int64_t row0 = 0; row0 < L.nx + 2; row0 += rows_per_chunk) {
+        const int64_t nrows = std::min(rows_per_chunk, L.nx + 2 - row0);
+        s->launches += launch_pack_rows(L, s->staging, ncomp, planes, plane_stride,
+                                        row0, nrows, s->code, zero_mode, s->stream);
+        CUDA_TRY(cudaMemcpyAsync(host + row0 * row_elems, s->staging,
+                                 size_t(nrows) * row_elems * sizeof(double),
+                                 cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PLB_OK;
+}
+
+int download_inner(plb_solver *s, double *host, int ncomp, const double *planes,
+                   int64_t plane_stride)
+{
+    const Layout &L = s->L;
+    const int64_t row_elems = L.ny * ncomp;
+    const int64_t rows_per_chunk =
+        std::max<int64_t>(1, int64_t(CHUNK_BYTES / (row_elems * sizeof(double))));
+    if (int rc = ensure_staging(s, size_t(rows_per_chunk) * row_elems * sizeof(double)))
+        return rc;
+    for (int64_t x0 = 0; x0 < L.nx; x0 += rows_per_chunk) {
+        const int64_t nrows = std::min(rows_per_chunk, L.nx - x0);
+        s->launches += launch_pack_inner(L, s->staging, ncomp, planes, plane_stride,
+                                         x0, nrows, s->stream);
+        CUDA_TRY(cudaMemcpyAsync(host + x0 * row_elems, s->staging,
+                                 size_t(nrows) * row_elems * sizeof(double),
+                                 cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PLB_OK;
+}
+
+// Per-direction link codes of fluid node (x, y); see LinkCode.
+struct Classifier {
+    const plb_solver *s;
+    int64_t nx, ny, nyp;
+    const uint8_t *solid;
+    const std::unordered_map<int64_t, int32_t> *element_of;   // ind*9+o -> e
+    const std::unordered_set<int64_t> *zg_cover;
+
+    bool is_solid(int64_t x, int64_t y) const
+    {
+        return solid[(x + 1) * nyp + (y + 1)] != 0;
+    }
+    uint64_t links(int64_t x, int64_t y) const
+    {
+        const int64_t ind = (x + 1) * nyp + (y + 1);
+        const bool edge = x == 0 || y == 0 || x == nx - 1 || y == ny - 1;
+        uint64_t out = 0;
+        for (int q = 1; q < Q; ++q) {
+            const int64_t tx = x + CX[q], ty = y + CY[q];
+            uint8_t code = LINK_PUSH;
+            bool done = false;
+            if (edge) {
+                const int64_t key = ind * Q + q;
+                if (zg_cover->count(key)) {
+                    code = LINK_ZG;
+                    done = true;
+                } else {
+                    auto it = element_of->find(key);
+                    if (it != element_of->end()) {
+                        code = uint8_t(LINK_ELEMENT0 + it->second);
+                        done = true;
+                    }
+                }
+            }
+            if (!done) {
+                if (is_solid(tx, ty)) {
+                    code = LINK_SOLID_BB;
+                } else {
+                    const bool x_out = tx < 0 || tx >= nx;
+                    const bool y_out = ty < 0 || ty >= ny;
+                    if (x_out || y_out) {
+                        bool reachable = true;
+                        if (x_out)
+                            reachable = tx < 0 ? s->cfg.left_neighbor != 0
+                                               : s->cfg.right_neighbor != 0;
+                        if (y_out && !s->cfg.y_periodic) reachable = false;
+                        code = !reachable ? LINK_ZERO
+                                          : (y_out ? LINK_WRAP : LINK_PUSH);
+                    }
+                }
+            }
+            out |= uint64_t(code) << (8 * (q - 1));
+        }
+        return out;
+    }
+};
+
+int run_zero_gradient(plb_solver *s, double *fout, cudaStream_t st)
+{
+    for (auto &z : s->zg_dev)
+        s->launches += launch_zero_gradient(fout, s->L.plane, z.first, z.second, st);
+    return PLB_OK;
+}
+
+int step_once(plb_solver *s, bool store)
+{
+    const Layout &L = s->L;
+    StepArgs a;
+    a.p = s->kp;
+    a.fin = s->f[s->cur];
+    a.fout = s->f[s->cur ^ 1];
+    a.code = s->code;
+    a.rho = s->rho();
+    a.ux = s->ux();
+    a.uy = s->uy();
+    a.collision = s->cfg.collision;
+    a.forcing = s->cfg.forcing;
+    a.store = store ? 1 : 0;
+    double *fout = a.fout;
+    const int32_t right_dirs[3] = {1, 5, 8}, left_dirs[3] = {3, 6, 7};
+    const bool faces = s->cfg.left_neighbor || s->cfg.right_neighbor;
+
+    if (!s->comm) {
+        s->launches += launch_bulk(a, 0, L.nx, s->variant, s->stream);
+        s->launches += launch_links(a, s->links_dev, s->n_links, s->elements_dev,
+                                    s->stream);
+        if (faces) {
+            // single rank: the periodic image is this rank's own ghost column
+            if (s->cfg.left_neighbor)
+                s->launches += launch_face_unpack(
+                    L, fout, 0, right_dirs, fout, 1 * L.plane + L.at(L.nx, 0),
+                    5 * L.plane + L.at(L.nx, 0), 8 * L.plane + L.at(L.nx, 0),
+                    s->mask_left, s->stream);
+            if (s->cfg.right_neighbor)
+                s->launches += launch_face_unpack(
+                    L, fout, L.nx - 1, left_dirs, fout, 3 * L.plane + L.at(-1, 0),
+                    6 * L.plane + L.at(-1, 0), 7 * L.plane + L.at(-1, 0),
+                    s->mask_right, s->stream);
+        }
+        run_zero_gradient(s, fout, s->stream);
+    } else {
+        // slab edges first, so that the face exchange overlaps the interior
+        s->launches += launch_bulk(a, 0, 1, s->variant, s->stream);
+        if (L.nx > 1)
+            s->launches += launch_bulk(a, L.nx - 1, L.nx, s->variant, s->stream);
+        s->launches += launch_links(a, s->links_dev, s->n_links, s->elements_dev,
+                                    s->stream);
+        CUDA_TRY(cudaEventRecord(s->ev_edge, s->stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->comm_stream, s->ev_edge, 0));
+        NCCL_TRY(g_nccl.GroupStart());
+        if (s->right_rank >= 0)
+            for (int j = 0; j < 3; ++j)
+                NCCL_TRY(g_nccl.Send(fout + right_dirs[j] * L.plane + L.at(L.nx, 0),
+                                     size_t(L.ny), ncclDouble, s->right_rank,
+                                     s->comm, s->comm_stream));
+        if (s->left_rank >= 0)
+            for (int j = 0; j < 3; ++j)
+                NCCL_TRY(g_nccl.Send(fout + left_dirs[j] * L.plane + L.at(-1, 0),
+                                     size_t(L.ny), ncclDouble, s->left_rank,
+                                     s->comm, s->comm_stream));
+        if (s->left_rank >= 0)
+            for (int j = 0; j < 3; ++j)
+                NCCL_TRY(g_nccl.Recv(s->recv_left + j * L.ny, size_t(L.ny),
+                                     ncclDouble, s->left_rank, s->comm,
+                                     s->comm_stream));
+        if (s->right_rank >= 0)
+            for (int j = 0; j < 3; ++j)
+                NCCL_TRY(g_nccl.Recv(s->recv_right + j * L.ny, size_t(L.ny),
+                                     ncclDouble, s->right_rank, s->comm,
+                                     s->comm_stream));
+        NCCL_TRY(g_nccl.GroupEnd());
+        if (s->left_rank >= 0)
+            s->launches += launch_face_unpack(L, fout, 0, right_dirs, s->recv_left,
+                                              0, L.ny, 2 * L.ny, s->mask_left,
+                                              s->comm_stream);
+        if (s->right_rank >= 0)
+            s->launches += launch_face_unpack(L, fout, L.nx - 1, left_dirs,
+                                              s->recv_right, 0, L.ny, 2 * L.ny,
+                                              s->mask_right, s->comm_stream);
+        CUDA_TRY(cudaEventRecord(s->ev_comm, s->comm_stream));
+        s->launches += launch_bulk(a, 1, L.nx - 1, s->variant, s->stream);
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
+        run_zero_gradient(s, fout, s->stream);
+    }
+    s->cur ^= 1;
+    s->steps_done += 1;
+    return PLB_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char *plb_last_error(void) { return g_error.c_str(); }
+
+int plb_create(const plb_config *c, plb_handle *out)
+{
+    if (!c || !out) return fail(PLB_ERR_INVALID, "null argument");
+    if (c->abi_version != PLB_ABI_VERSION)
+        return fail(PLB_ERR_INVALID, "abi_version %d != %d", c->abi_version,
+                    PLB_ABI_VERSION);
+    if (c->nx < 1 || c->ny < 1)
+        return fail(PLB_ERR_INVALID, "nx, ny must be >= 1 (got %lld, %lld)",
+                    (long long)c->nx, (long long)c->ny);
+    if (c->nx > 2000000000LL || c->ny > 2000000000LL)
+        return fail(PLB_ERR_INVALID, "nx, ny must fit int32");
+    if (c->collision != PLB_BGK && c->collision != PLB_MRT)
+        return fail(PLB_ERR_INVALID, "unknown collision model %d", c->collision);
+    if (c->forcing < 0 || c->forcing > 2)
+        return fail(PLB_ERR_INVALID, "unknown forcing model %d", c->forcing);
+
+    int n_dev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n_dev));
+    if (c->device < 0 || c->device >= n_dev)
+        return fail(PLB_ERR_CUDA, "CUDA device %d not available (%d visible)",
+                    c->device, n_dev);
+    CUDA_TRY(cudaSetDevice(c->device));
+
+    plb_solver *s = new plb_solver();
+    s->cfg = *c;
+    Layout &L = s->L;
+    L.nx = c->nx;
+    L.ny = c->ny;
+    L.y0 = 16;
+    L.pitch = ((L.y0 + L.ny + 1) + 15) / 16 * 16;
+    L.plane = (L.nx + 2) * L.pitch;
+    KParams &p = s->kp;
+    p.L = L;
+    p.omega = c->omega;
+    p.gx = c->gravity[0];
+    p.gy = c->gravity[1];
+    p.inv_cs_2 = c->inv_cs_2;
+    p.inv_cs_4 = c->inv_cs_4;
+    p.eps = c->float_min;
+    for (int k = 0; k < Q; ++k) {
+        p.w[k] = c->weights[k];
+        p.s[k] = c->mrt_rates[k];
+    }
+    if (const char *v = getenv("PLB_KERNEL"))
+        s->variant = (strcmp(v, "scalar") == 0) ? 0 : 1;
+
+    auto cleanup = [&](int rc) {
+        plb_destroy(s);
+        return rc;
+    };
+#define TRY_OR_CLEAN(expr)                                                    \
+    do {                                                                      \
+        cudaError_t err__ = (expr);                                           \
+        if (err__ != cudaSuccess)                                             \
+            return cleanup(fail(err__ == cudaErrorMemoryAllocation            \
+                                    ? PLB_ERR_NOMEM : PLB_ERR_CUDA,           \
+                                "%s failed: %s", #expr,                       \
+                                cudaGetErrorString(err__)));                  \
+    } while (0)
+    TRY_OR_CLEAN(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto &e : s->events) TRY_OR_CLEAN(cudaEventCreate(&e));
+    const size_t plane_bytes = size_t(L.plane) * sizeof(double);
+    for (int i = 0; i < 2; ++i) {
+        TRY_OR_CLEAN(cudaMalloc(&s->f[i], Q * plane_bytes));
+        TRY_OR_CLEAN(cudaMemsetAsync(s->f[i], 0, Q * plane_bytes, s->stream));
+    }
+    TRY_OR_CLEAN(cudaMalloc(&s->mom, 3 * plane_bytes));
+    TRY_OR_CLEAN(cudaMemsetAsync(s->mom, 0, 3 * plane_bytes, s->stream));
+    TRY_OR_CLEAN(cudaMalloc(&s->code, size_t(L.plane)));
+    TRY_OR_CLEAN(cudaMemsetAsync(s->code, NODE_GHOST, size_t(L.plane), s->stream));
+    TRY_OR_CLEAN(cudaStreamSynchronize(s->stream));
+#undef TRY_OR_CLEAN
+    s->solid_host.assign(size_t((L.nx + 2) * (L.ny + 2)), 0);
+    *out = s;
+    return PLB_OK;
+}
+
+void plb_destroy(plb_handle s)
+{
+    if (!s) return;
+    cudaSetDevice(s->cfg.device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
+    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    for (int i = 0; i < 2; ++i) cudaFree(s->f[i]);
+    cudaFree(s->mom);
+    cudaFree(s->mom_old);
+    cudaFree(s->res_partials);
+    cudaFree(s->res_out);
+    cudaFree(s->code);
+    cudaFree(s->staging);
+    cudaFree(s->flush_buf);
+    cudaFree(s->elements_dev);
+    cudaFree(s->links_dev);
+    for (auto &z : s->zg_dev) cudaFree(z.first);
+    cudaFree(s->mask_left);
+    cudaFree(s->mask_right);
+    cudaFree(s->recv_left);
+    cudaFree(s->recv_right);
+    for (auto &e : s->events)
+        if (e) cudaEventDestroy(e);
+    if (s->ev_edge) cudaEventDestroy(s->ev_edge);
+    if (s->ev_comm) cudaEventDestroy(s->ev_comm);
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int plb_add_boundary_element(plb_handle s, int32_t bc_type,
+                             const int64_t *boundary_nodes, int64_t n_nodes,
+                             const int64_t out_list[3], const int64_t inv_list[3],
+                             const int64_t normal[2], const double vector_fluid[2],
+                             double scalar_fluid)
+{
+    if (!s) return fail(PLB_ERR_INVALID, "null handle");
+    if (s->finalized)
+        return fail(PLB_ERR_STATE, "geometry already finalized");
+    if (bc_type < PLB_BC_BOUNCE_BACK || bc_type > PLB_BC_ZERO_GRADIENT)
+        return fail(PLB_ERR_INVALID, "unknown boundary type %d", bc_type);
+    if (n_nodes < 0 || (n_nodes > 0 && !boundary_nodes))
+        return fail(PLB_ERR_INVALID, "bad boundary node list");
+    if ((int)s->elements.size() >= MAX_ELEMENTS)
+        return fail(PLB_ERR_INVALID, "more than %d boundary elements", MAX_ELEMENTS);
+    const int64_t size = (s->L.nx + 2) * (s->L.ny + 2);
+    ElementHost e;
+    e.type = bc_type;
+    e.nodes.assign(boundary_nodes, boundary_nodes + n_nodes);
+    for (int64_t n : e.nodes)
+        if (n < 0 || n >= size)
+            return fail(PLB_ERR_INVALID, "boundary node %lld out of range",
+                        (long long)n);
+    for (int j = 0; j < 3; ++j) {
+        if (out_list[j] < 1 || out_list[j] >= Q || inv_list[j] != INV[out_list[j]])
+            return fail(PLB_ERR_INVALID,
+                        "out_list/inv_list are not opposite D2Q9 directions");
+        e.out[j] = out_list[j];
+        e.inv[j] = inv_list[j];
+    }
+    e.normal[0] = normal[0];
+    e.normal[1] = normal[1];
+    e.vector[0] = vector_fluid ? vector_fluid[0] : 0.0;
+    e.vector[1] = vector_fluid ? vector_fluid[1] : 0.0;
+    e.scalar = scalar_fluid;
+    s->elements.push_back(std::move(e));
+    return PLB_OK;
+}
+
+int plb_finalize_geometry(plb_handle s)
+{
+    if (!s) return fail(PLB_ERR_INVALID, "null handle");
+    if (s->finalized) return fail(PLB_ERR_STATE, "geometry already finalized");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    const Layout &L = s->L;
+    const int64_t nx = L.nx, ny = L.ny, nyp = ny + 2;
+
+    // links owned by boundary elements; later elements win, zero_gradient
+    // elements are a final pass (see oracle_set_boundary)
+    std::unordered_map<int64_t, int32_t> element_of;
+    std::unordered_set<int64_t> zg_cover;
+    for (size_t e = 0; e < s->elements.size(); ++e) {
+        const ElementHost &el = s->elements[e];
+        if (el.type == PLB_BC_PERIODIC) continue;
+        for (int64_t ind : el.nodes)
+            for (int j = 0; j < 3; ++j) {
+                if (el.type == PLB_BC_ZERO_GRADIENT) zg_cover.insert(ind * Q + el.out[j]);
+                else element_of[ind * Q + el.out[j]] = int32_t(e);
+            }
+    }
+    Classifier cls{s, nx, ny, nyp, s->solid_host.data(), &element_of, &zg_cover};
+
+    // rows (reference x) that contain any solid node, ghost ring included
+    std::vector<uint8_t> row_has_solid(size_t(nx + 2), 0);
+    for (int64_t r = 0; r < nx + 2; ++r) {
+        const uint8_t *row = s->solid_host.data() + r * nyp;
+        row_has_solid[r] = memchr(row, 1, size_t(nyp)) != nullptr;
+        if (!row_has_solid[r])
+            for (int64_t j = 0; j < nyp; ++j)
+                if (row[j]) { row_has_solid[r] = 1; break; }
+    }
+
+    std::vector<uint8_t> code(size_t(L.plane), NODE_GHOST);
+    std::vector<LinkNode> link_nodes;
+    int64_t n_bulk = 0, n_solid = 0;
+    for (int64_t x = 0; x < nx; ++x) {
+        uint8_t *crow = code.data() + L.at(x, 0);
+        const bool near_solid =
+            row_has_solid[x] || row_has_solid[x + 1] || row_has_solid[x + 2];
+        const bool edge_row = x == 0 || x == nx - 1;
+        for (int64_t y = 0; y < ny; ++y) {
+            if (!near_solid && !edge_row && y > 0 && y < ny - 1) {
+                crow[y] = NODE_BULK;
+                ++n_bulk;
+                continue;
+            }
+            if (cls.is_solid(x, y)) {
+                crow[y] = NODE_SOLID;
+                ++n_solid;
+                continue;
+            }
+            const uint64_t lk = cls.links(x, y);
+            if (lk == 0) {
+                crow[y] = NODE_BULK;
+                ++n_bulk;
+            } else {
+                crow[y] = NODE_LINK;
+                link_nodes.push_back(LinkNode{int32_t(x), int32_t(y), lk});
+            }
+        }
+    }
+    s->n_bulk = n_bulk;
+    s->n_solid = n_solid;
+
+    // slab-face acceptance masks: slot (node, k) is fed from across the face
+    // iff the node is fluid and its own link in direction inv(k) is a push
+    std::vector<uint8_t> mask_l(size_t(ny), 0), mask_r(size_t(ny), 0);
+    const int right_dirs[3] = {1, 5, 8}, left_dirs[3] = {3, 6, 7};
+    for (int64_t y = 0; y < ny; ++y) {
+        if (s->cfg.left_neighbor && !cls.is_solid(0, y)) {
+            const uint64_t lk = cls.links(0, y);
+            for (int j = 0; j < 3; ++j) {
+                const int c = int((lk >> (8 * (INV[right_dirs[j]] - 1))) & 0xff);
+                if (c == LINK_PUSH || c == LINK_WRAP) mask_l[y] |= uint8_t(1 << j);
+            }
+        }
+        if (s->cfg.right_neighbor && !cls.is_solid(nx - 1, y)) {
+            const uint64_t lk = cls.links(nx - 1, y);
+            for (int j = 0; j < 3; ++j) {
+                const int c = int((lk >> (8 * (INV[left_dirs[j]] - 1))) & 0xff);
+                if (c == LINK_PUSH || c == LINK_WRAP) mask_r[y] |= uint8_t(1 << j);
+            }
+        }
+    }
+
+    // device copies
+    CUDA_TRY(cudaMemcpy(s->code, code.data(), code.size(), cudaMemcpyHostToDevice));
+    s->n_links = int64_t(link_nodes.size());
+    if (s->n_links) {
+        CUDA_TRY(cudaMalloc(&s->links_dev, link_nodes.size() * sizeof(LinkNode)));
+        CUDA_TRY(cudaMemcpy(s->links_dev, link_nodes.data(),
+                            link_nodes.size() * sizeof(LinkNode),
+                            cudaMemcpyHostToDevice));
+    }
+    std::vector<ElementDev> edev(std::max<size_t>(1, s->elements.size()));
+    for (size_t e = 0; e < s->elements.size(); ++e) {
+        const ElementHost &el = s->elements[e];
+        edev[e] = ElementDev{el.type, int32_t(el.normal[0]), int32_t(el.normal[1]),
+                             0, el.vector[0], el.vector[1], el.scalar};
+    }
+    CUDA_TRY(cudaMalloc(&s->elements_dev, edev.size() * sizeof(ElementDev)));
+    CUDA_TRY(cudaMemcpy(s->elements_dev, edev.data(), edev.size() * sizeof(ElementDev),
+                        cudaMemcpyHostToDevice));
+    for (const ElementHost &el : s->elements) {
+        if (el.type != PLB_BC_ZERO_GRADIENT) continue;
+        std::vector<ZgLink> zl;
+        for (int64_t ind : el.nodes) {
+            if (s->solid_host[size_t(ind)]) continue;
+            const int64_t x = ind / nyp - 1, y = ind % nyp - 1;
+            if (x < 0 || x >= nx || y < 0 || y >= ny) continue;
+            for (int j = 0; j < 3; ++j)
+                zl.push_back(ZgLink{L.at(x, y),
+                                    L.at(x + el.normal[0], y + el.normal[1]),
+                                    int32_t(el.inv[j]), 0});
+        }
+        ZgLink *dev = nullptr;
+        if (!zl.empty()) {
+            CUDA_TRY(cudaMalloc(&dev, zl.size() * sizeof(ZgLink)));
+            CUDA_TRY(cudaMemcpy(dev, zl.data(), zl.size() * sizeof(ZgLink),
+                                cudaMemcpyHostToDevice));
+        }
+        s->zg_dev.emplace_back(dev, int64_t(zl.size()));
+    }
+    CUDA_TRY(cudaMalloc(&s->mask_left, size_t(ny)));
+    CUDA_TRY(cudaMalloc(&s->mask_right, size_t(ny)));
+    CUDA_TRY(cudaMemcpy(s->mask_left, mask_l.data(), size_t(ny), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(s->mask_right, mask_r.data(), size_t(ny), cudaMemcpyHostToDevice));
+    s->finalized = true;
+    return PLB_OK;
+}
+
+int plb_upload(plb_handle s, int32_t field, const void *host, size_t bytes)
+{
+    if (!s || !host) return fail(PLB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    const Layout &L = s->L;
+    const size_t size = size_t((L.nx + 2) * (L.ny + 2));
+    switch (field) {
+    case PLB_SOLID:
+        if (bytes != size) return fail(PLB_ERR_INVALID, "PLB_SOLID expects %zu bytes", size);
+        if (s->finalized) return fail(PLB_ERR_STATE, "geometry already finalized");
+        memcpy(s->solid_host.data(), host, size);
+        return PLB_OK;
+    case PLB_DENSITY:
+        if (bytes != size * 8) return fail(PLB_ERR_INVALID, "PLB_DENSITY expects %zu bytes", size * 8);
+        return upload_padded(s, static_cast<const double *>(host), 1, s->rho(), L.plane);
+    case PLB_VELOCITY:
+        if (bytes != size * 16) return fail(PLB_ERR_INVALID, "PLB_VELOCITY expects %zu bytes", size * 16);
+        return upload_padded(s, static_cast<const double *>(host), 2, s->ux(), L.plane);
+    case PLB_POP:
+        if (bytes != size * 72) return fail(PLB_ERR_INVALID, "PLB_POP expects %zu bytes", size * 72);
+        return upload_padded(s, static_cast<const double *>(host), Q, s->f[s->cur], L.plane);
+    default:
+        return fail(PLB_ERR_INVALID, "field %d cannot be uploaded", field);
+    }
+}
+
+int plb_download(plb_handle s, int32_t field, void *host, size_t bytes)
+{
+    if (!s || !host) return fail(PLB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    const Layout &L = s->L;
+    const size_t size = size_t((L.nx + 2) * (L.ny + 2));
+    const size_t inner = size_t(L.nx * L.ny);
+    double *out = static_cast<double *>(host);
+    switch (field) {
+    case PLB_SOLID:
+        if (bytes != size) return fail(PLB_ERR_INVALID, "PLB_SOLID expects %zu bytes", size);
+        memcpy(host, s->solid_host.data(), size);
+        return PLB_OK;
+    case PLB_DENSITY:
+        if (bytes != size * 8) return fail(PLB_ERR_INVALID, "PLB_DENSITY expects %zu bytes", size * 8);
+        return download_padded(s, out, 1, s->rho(), L.plane, 0);
+    case PLB_VELOCITY:
+        if (bytes != size * 16) return fail(PLB_ERR_INVALID, "PLB_VELOCITY expects %zu bytes", size * 16);
+        return download_padded(s, out, 2, s->ux(), L.plane, 0);
+    case PLB_POP:
+        if (bytes != size * 72) return fail(PLB_ERR_INVALID, "PLB_POP expects %zu bytes", size * 72);
+        return download_padded(s, out, Q, s->f[s->cur], L.plane, 1);
+    case PLB_DENSITY_INNER:
+        if (bytes != inner * 8) return fail(PLB_ERR_INVALID, "PLB_DENSITY_INNER expects %zu bytes", inner * 8);
+        return download_inner(s, out, 1, s->rho(), L.plane);
+    case PLB_VELOCITY_INNER:
+        if (bytes != inner * 16) return fail(PLB_ERR_INVALID, "PLB_VELOCITY_INNER expects %zu bytes", inner * 16);
+        return download_inner(s, out, 2, s->ux(), L.plane);
+    default:
+        return fail(PLB_ERR_INVALID, "field %d cannot be downloaded", field);
+    }
+}
+
+int plb_initialize_pop(plb_handle s)
+{
+    if (!s) return fail(PLB_ERR_INVALID, "null handle");
+    if (!s->finalized) return fail(PLB_ERR_STATE, "plb_finalize_geometry not called");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    s->launches += launch_init_pop(s->kp, s->f[s->cur], s->code, s->rho(), s->ux(),
+                                   s->uy(), s->stream);
+    CUDA_TRY(cudaMemsetAsync(s->f[s->cur ^ 1], 0, size_t(Q) * s->L.plane * sizeof(double),
+                             s->stream));
+    CUDA_TRY(cudaGetLastError());
+    return PLB_OK;
+}
+
+int plb_step(plb_handle s, int64_t n_steps, int32_t store_moments)
+{
+    if (!s) return fail(PLB_ERR_INVALID, "null handle");
+    if (!s->finalized) return fail(PLB_ERR_STATE, "plb_finalize_geometry not called");
+    if (n_steps < 0) return fail(PLB_ERR_INVALID, "n_steps < 0");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    for (int64_t i = 0; i < n_steps; ++i)
+        if (int rc = step_once(s, store_moments && i == n_steps - 1)) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return PLB_OK;
+}
+
+int plb_sync(plb_handle s)
+{
+    if (!s) return fail(PLB_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (s->comm_stream) CUDA_TRY(cudaStreamSynchronize(s->comm_stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return PLB_OK;
+}
+
+int plb_residue_sums(plb_handle s, double out[6])
+{
+    if (!s || !out) return fail(PLB_ERR_INVALID, "null argument");
+    if (!s->finalized) return fail(PLB_ERR_STATE, "plb_finalize_geometry not called");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    const int n_blocks = 148 * 4;
+    const size_t plane_bytes = size_t(s->L.plane) * sizeof(double);
+    if (!s->mom_old) {
+        CUDA_TRY(cudaMalloc(&s->mom_old, 3 * plane_bytes));
+        CUDA_TRY(cudaMemsetAsync(s->mom_old, 0, 3 * plane_bytes, s->stream));
+        CUDA_TRY(cudaMalloc(&s->res_partials, size_t(n_blocks) * 6 * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&s->res_out, 6 * sizeof(double)));
+    }
+    s->launches += launch_residue(s->L, s->code, s->rho(), s->ux(), s->uy(), s->mom_old,
+                                  s->mom_old + s->L.plane, s->mom_old + 2 * s->L.plane,
+                                  s->res_partials, n_blocks, s->res_out, s->stream);
+    CUDA_TRY(cudaMemcpyAsync(out, s->res_out, 6 * sizeof(double), cudaMemcpyDeviceToHost,
+                             s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return PLB_OK;
+}
+
+int plb_comm_unique_id(void *id128)
+{
+    if (!id128) return fail(PLB_ERR_INVALID, "null argument");
+    if (int rc = load_nccl()) return rc;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return PLB_OK;
+}
+
+int plb_comm_init(plb_handle s, const void *id128, int32_t rank, int32_t n_ranks,
+                  int32_t left_rank, int32_t right_rank)
+{
+    if (!s || !id128) return fail(PLB_ERR_INVALID, "null argument");
+    if (s->comm) return fail(PLB_ERR_STATE, "communicator already initialised");
+    if (n_ranks < 2 || rank < 0 || rank >= n_ranks)
+        return fail(PLB_ERR_INVALID, "bad rank %d of %d", rank, n_ranks);
+    if (left_rank >= n_ranks || right_rank >= n_ranks || left_rank == rank ||
+        right_rank == rank)
+        return fail(PLB_ERR_INVALID, "bad neighbour ranks %d, %d", left_rank, right_rank);
+    if ((left_rank >= 0) != (s->cfg.left_neighbor != 0) ||
+        (right_rank >= 0) != (s->cfg.right_neighbor != 0))
+        return fail(PLB_ERR_INVALID,
+                    "neighbour ranks disagree with plb_config.left/right_neighbor");
+    if (int rc = load_nccl()) return rc;
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    NCCL_TRY(g_nccl.CommInitRank(&s->comm, n_ranks, id, rank));
+    s->rank = rank;
+    s->n_ranks = n_ranks;
+    s->left_rank = left_rank;
+    s->right_rank = right_rank;
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, hi));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_edge, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&s->recv_left, size_t(3 * s->L.ny) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s->recv_right, size_t(3 * s->L.ny) * sizeof(double)));
+    return PLB_OK;
+}
+
+int plb_event_record(plb_handle s, int32_t slot)
+{
+    if (!s || slot < 0 || slot >= 8) return fail(PLB_ERR_INVALID, "bad event slot");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(cudaEventRecord(s->events[slot], s->stream));
+    return PLB_OK;
+}
+
+int plb_event_elapsed_ms(plb_handle s, int32_t a, int32_t b, float *ms)
+{
+    if (!s || !ms || a < 0 || a >= 8 || b < 0 || b >= 8)
+        return fail(PLB_ERR_INVALID, "bad event slot");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(cudaEventSynchronize(s->events[b]));
+    CUDA_TRY(cudaEventElapsedTime(ms, s->events[a], s->events[b]));
+    return PLB_OK;
+}
+
+int64_t plb_kernel_launches(plb_handle s, int32_t reset)
+{
+    if (!s) return 0;
+    const int64_t n = s->launches;
+    if (reset) s->launches = 0;
+    return n;
+}
+
+int plb_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(PLB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return PLB_OK;
+}
+
+int plb_host_free(void *ptr)
+{
+    CUDA_TRY(cudaFreeHost(ptr));
+    return PLB_OK;
+}
+
+int plb_flush_l2(plb_handle s)
+{
+    if (!s) return fail(PLB_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    const int64_t n = (int64_t(256) << 20) / 8;   // 256 MiB > 126 MB L2
+    if (!s->flush_buf) CUDA_TRY(cudaMalloc(&s->flush_buf, size_t(n) * 8));
+    s->launches += launch_fill(s->flush_buf, n, 0.0, s->stream);
+    CUDA_TRY(cudaGetLastError());
+    return PLB_OK;
+}
+
+}  // extern "C"

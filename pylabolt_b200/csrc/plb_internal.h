@@ -1,0 +1,127 @@
+// plb_internal.h -- structures shared by the host side (plb_api.cu) and the
+// kernels (plb_kernels.cu) of libplb.  Not part of the ABI (include/plb.h is).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace plb {
+
+constexpr int Q = 9;
+
+// D2Q9 direction tables, pylabolt/base/lattice.py:50-60.
+#define PLB_CX_LIST {0, 1, 0, -1, 0, 1, -1, -1, 1}
+#define PLB_CY_LIST {0, 0, 1, 0, -1, 1, 1, -1, -1}
+#define PLB_INV_LIST {0, 3, 4, 1, 2, 7, 8, 5, 6}
+
+// Device layout of one scalar plane (a population k, rho, ux, uy or the node
+// codes): (nx + 2) rows of `pitch` elements, y contiguous.  Interior node
+// (x, y), x in [0, nx), y in [0, ny), lives at (x + 1) * pitch + y0 + y, so
+// y = 0 is 128-byte aligned (y0 = 16 doubles) and every row start is too
+// (pitch is a multiple of 16).  The ghost ring of the reference layout maps
+// to x = -1, nx and y = -1, ny.
+struct Layout {
+    int64_t nx, ny;
+    int64_t pitch;   // elements per row
+    int64_t plane;   // elements per plane = (nx + 2) * pitch
+    int32_t y0;      // column of interior y = 0
+    __host__ __device__ int64_t at(int64_t x, int64_t y) const {
+        return (x + 1) * pitch + y0 + y;
+    }
+};
+
+// Constants used verbatim by the kernels (values computed by the caller the
+// way the reference computes them, see plb_config in include/plb.h).
+struct KParams {
+    Layout L;
+    double omega, gx, gy, inv_cs_2, inv_cs_4, eps;
+    double w[Q];
+    double s[Q];   // MRT relaxation rates
+};
+
+// Node classes in the code plane.
+enum NodeCode : uint8_t {
+    NODE_BULK = 0,    // fluid, all 8 pushes go to plain neighbours
+    NODE_LINK = 1,    // fluid, handled by the link-list kernel
+    NODE_SOLID = 2,
+    NODE_GHOST = 3    // ghost ring and alignment padding
+};
+
+// Per-direction treatment of a link node's outgoing population q = 1..8,
+// one byte each, packed little-endian into a uint64 (byte q-1).
+enum LinkCode : uint8_t {
+    LINK_PUSH = 0,       // f'[i + c_q, q] = g_q
+    LINK_SOLID_BB = 1,   // halfway bounce back off a solid node (moving wall)
+    LINK_ZERO = 2,       // uncovered non-periodic ghost: f'[i, inv q] = 0
+    LINK_WRAP = 3,       // push with the y index wrapped (y-periodic)
+    LINK_ZG = 4,         // zero_gradient element: written by the zg pass
+    LINK_ELEMENT0 = 8    // 8 + e: boundary element e (bounce_back,
+                         // fixed_velocity, fixed_pressure)
+};
+constexpr int MAX_ELEMENTS = 247;
+
+struct ElementDev {
+    int32_t type;        // enum plb_bc_type
+    int32_t normal_x, normal_y;
+    int32_t pad;
+    double v0, v1;       // vector_fluid
+    double scalar;       // scalar_fluid
+};
+
+struct LinkNode {
+    int32_t x, y;        // interior coordinates
+    uint64_t links;      // 8 LinkCode bytes
+};
+
+// One zero_gradient copy: f'[v][dst] = f'[v][src].
+struct ZgLink {
+    int64_t dst, src;
+    int32_t v;
+    int32_t pad;
+};
+
+struct StepArgs {
+    KParams p;
+    const double *fin;
+    double *fout;
+    const uint8_t *code;
+    double *rho, *ux, *uy;   // moment planes (ux/uy also hold solid velocities)
+    int32_t collision, forcing, store;
+};
+
+// ---- launchers implemented in plb_kernels.cu ---------------------------
+// All return the number of kernels launched (0 if nothing to do).
+int launch_bulk(const StepArgs &a, int64_t x_begin, int64_t x_end, int variant,
+                cudaStream_t stream);
+int launch_links(const StepArgs &a, const LinkNode *nodes, int64_t n_nodes,
+                 const ElementDev *elements, cudaStream_t stream);
+int launch_zero_gradient(double *fout, int64_t plane, const ZgLink *links,
+                         int64_t n_links, cudaStream_t stream);
+// Copies the three face populations from `src` (three rows of ny doubles,
+// src_stride apart) into column x_col of fout where mask bit j is set.
+int launch_face_unpack(const Layout &L, double *fout, int64_t x_col,
+                       const int32_t dirs[3], const double *src,
+                       int64_t src_stride0, int64_t src_stride1,
+                       int64_t src_stride2, const uint8_t *mask,
+                       cudaStream_t stream);
+int launch_init_pop(const KParams &p, double *f, const uint8_t *code,
+                    const double *rho, const double *ux, const double *uy,
+                    cudaStream_t stream);
+// reference-layout (padded AoS) <-> device planes, rows [row0, row0 + nrows)
+// of the padded array (row = x + 1).
+int launch_unpack_rows(const Layout &L, const double *staging, int ncomp,
+                       double *planes, int64_t plane_stride, int64_t row0,
+                       int64_t nrows, cudaStream_t stream);
+int launch_pack_rows(const Layout &L, double *staging, int ncomp,
+                     const double *planes, int64_t plane_stride, int64_t row0,
+                     int64_t nrows, const uint8_t *code, int zero_mode,
+                     cudaStream_t stream);
+int launch_pack_inner(const Layout &L, double *staging, int ncomp,
+                      const double *planes, int64_t plane_stride, int64_t x0,
+                      int64_t nrows, cudaStream_t stream);
+int launch_residue(const Layout &L, const uint8_t *code, const double *rho,
+                   const double *ux, const double *uy, double *rho_old,
+                   double *ux_old, double *uy_old, double *partials,
+                   int n_blocks, double *out6, cudaStream_t stream);
+int launch_fill(double *buf, int64_t n, double value, cudaStream_t stream);
+
+}  // namespace plb

@@ -1,0 +1,551 @@
+// plb_kernels.cu -- sm_100a kernels of the fluidLB step.
+//
+// One time step of the reference (pylabolt/solvers/fluidLB.py:206-253) makes
+// five full passes over array-of-structures fields.  Here it is ONE pass:
+// every fluid node reads its nine populations (structure of arrays, fully
+// coalesced), computes rho / u / force, collides in registers and PUSHES the
+// post-collision populations into the second lattice.
+// 144 B per node per step is all that touches HBM, plus one code byte.
+//
+//   k_bulk_vec2 / k_bulk_scalar : nodes whose eight neighbours are plain
+//                                 fluid nodes (NODE_BULK) -- >99.9 % of a
+//                                 large lattice; no flags beyond the code byte
+//   k_links                     : the O(perimeter) NODE_LINK nodes (domain
+//                                 edges, obstacle surfaces) from a list, with
+//                                 per-direction link codes: halfway bounce
+//                                 back, moving wall, anti-bounce-back
+//                                 pressure, periodic wrap, uncovered ghost
+//   k_zero_gradient             : thin pass for zero_gradient elements
+//   k_face_unpack               : slab-face / periodic-x delivery of the
+//                                 three populations that cross a face
+#include "plb_collide.cuh"
+
+namespace plb {
+
+// ---------------------------------------------------------------------------
+// memory access helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld2(const double *p)
+{
+    return *reinterpret_cast<const double2 *>(p);
+}
+__device__ __forceinline__ void st2(double *p, double a, double b)
+{
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+}
+
+// ---------------------------------------------------------------------------
+// one bulk node, scalar accesses
+// ---------------------------------------------------------------------------
+template <int COLL, int FORCING, bool STORE>
+__device__ __forceinline__ void bulk_node(const StepArgs &a, int64_t idx)
+{
+    const int64_t plane = a.p.L.plane, pitch = a.p.L.pitch;
+    double f[Q], g[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) f[k] = a.fin[k * plane + idx];
+    const Moments m = collide<COLL, FORCING>(a.p, f, g);
+    if constexpr (STORE) {
+        a.rho[idx] = m.rho;
+        a.ux[idx] = m.ux;
+        a.uy[idx] = m.uy;
+    }
+#pragma unroll
+    for (int k = 0; k < Q; ++k)
+        a.fout[k * plane + idx + d_cx[k] * pitch + d_cy[k]] = g[k];
+}
+
+template <int COLL, int FORCING, bool STORE>
+__global__ void __launch_bounds__(256)
+k_bulk_scalar(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
+{
+    const int64_t row = blockIdx.x / chunks_per_row;
+    const int32_t chunk = blockIdx.x - row * chunks_per_row;
+    const int64_t y = int64_t(chunk) * 256 + threadIdx.x;
+    if (y >= a.p.L.ny) return;
+    const int64_t idx = a.p.L.at(x_begin + row, y);
+    if (a.code[idx] != NODE_BULK) return;
+    bulk_node<COLL, FORCING, STORE>(a, idx);
+}
+
+// ---------------------------------------------------------------------------
+// two nodes per thread, 128-bit loads and stores
+// ---------------------------------------------------------------------------
+// A warp owns 64 consecutive y of one row.  Loads are aligned double2.  The
+// three populations with c_y = 0 are stored as aligned double2 into rows
+// x-1, x, x+1.  For c_y = +-1 the destination is shifted by one double, so the
+// aligned pair [y, y+1] of the destination row is assembled from this lane
+// and its neighbour with one shuffle; only the two ends of the 64-node run
+// fall back to 8-byte stores.  Any warp that contains a non-bulk node takes
+// the scalar path (domain edges, obstacle surfaces).
+template <int COLL, int FORCING, bool STORE>
+__global__ void __launch_bounds__(128)
+k_bulk_vec2(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
+{
+    const Layout &L = a.p.L;
+    const int64_t row = blockIdx.x / chunks_per_row;
+    const int32_t chunk = blockIdx.x - row * chunks_per_row;
+    const int64_t y = int64_t(chunk) * 256 + 2 * threadIdx.x;
+    const int64_t idx = L.at(x_begin + row, y);
+    const int lane = threadIdx.x & 31;
+
+    uint16_t codes = 0x0303;
+    if (y + 1 < L.ny)
+        codes = *reinterpret_cast<const uint16_t *>(a.code + idx);
+    else if (y < L.ny)
+        codes = uint16_t(a.code[idx]) | 0x0300;
+
+    if (!__all_sync(0xffffffffu, codes == 0)) {
+        if ((codes & 0xff) == NODE_BULK)
+            bulk_node<COLL, FORCING, STORE>(a, idx);
+        if ((codes >> 8) == NODE_BULK)
+            bulk_node<COLL, FORCING, STORE>(a, idx + 1);
+        return;
+    }
+
+    const int64_t plane = L.plane, pitch = L.pitch;
+    double fa[Q], fb[Q], ga[Q], gb[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+        const double2 v = ld2(a.fin + k * plane + idx);
+        fa[k] = v.x;
+        fb[k] = v.y;
+    }
+    const Moments ma = collide<COLL, FORCING>(a.p, fa, ga);
+    const Moments mb = collide<COLL, FORCING>(a.p, fb, gb);
+    if constexpr (STORE) {
+        st2(a.rho + idx, ma.rho, mb.rho);
+        st2(a.ux + idx, ma.ux, mb.ux);
+        st2(a.uy + idx, ma.uy, mb.uy);
+    }
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+        double *dst = a.fout + k * plane + idx + d_cx[k] * pitch;
+        if (d_cy[k] == 0) {
+            st2(dst, ga[k], gb[k]);
+        } else if (d_cy[k] == 1) {
+            // values move to y+1, y+2: pair [y, y+1] = (left lane's b, own a)
+            const double up = __shfl_up_sync(0xffffffffu, gb[k], 1);
+            if (lane != 0) st2(dst, up, ga[k]);
+            else dst[1] = ga[k];
+            if (lane == 31) dst[2] = gb[k];
+        } else {
+            // values move to y-1, y: pair [y, y+1] = (own b, right lane's a)
+            const double dn = __shfl_down_sync(0xffffffffu, ga[k], 1);
+            if (lane != 31) st2(dst, gb[k], dn);
+            else dst[0] = gb[k];
+            if (lane == 0) dst[-1] = ga[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// link nodes
+// ---------------------------------------------------------------------------
+// velocity[ind] as the reference's fixed_pressure kernel would read it
+// (cpu/fluid_boundary_kernels.py:131-140): phase-4 velocity of this step for a
+// fluid node (recomputed from the intact old lattice), the stored rigid-body
+// velocity for a solid node, zero on the ghost ring.
+__device__ __forceinline__ void node_velocity(const StepArgs &a, int64_t idx,
+                                              double &ux, double &uy)
+{
+    const uint8_t c = a.code[idx];
+    if (c == NODE_BULK || c == NODE_LINK) {
+        double f[Q];
+#pragma unroll
+        for (int k = 0; k < Q; ++k) f[k] = a.fin[k * a.p.L.plane + idx];
+        const Moments m = moments(a.p, f);
+        ux = m.ux;
+        uy = m.uy;
+    } else {
+        ux = a.ux[idx];
+        uy = a.uy[idx];
+    }
+}
+
+template <int COLL, int FORCING, bool STORE>
+__global__ void __launch_bounds__(128)
+k_links(StepArgs a, const LinkNode *__restrict__ nodes, int64_t n_nodes,
+        const ElementDev *__restrict__ elements)
+{
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const LinkNode nd = nodes[i];
+    const Layout &L = a.p.L;
+    const int64_t plane = L.plane, pitch = L.pitch;
+    const int64_t idx = L.at(nd.x, nd.y);
+
+    double f[Q], g[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) f[k] = a.fin[k * plane + idx];
+    const Moments m = collide<COLL, FORCING>(a.p, f, g);
+    if constexpr (STORE) {
+        a.rho[idx] = m.rho;
+        a.ux[idx] = m.ux;
+        a.uy[idx] = m.uy;
+    }
+    a.fout[idx] = g[0];   // pop_new[ind, 0] = pop[ind, 0], streaming_kernels.py:34
+
+#pragma unroll
+    for (int q = 1; q < Q; ++q) {
+        const int code = int((nd.links >> (8 * (q - 1))) & 0xff);
+        const int cx = d_cx[q], cy = d_cy[q], qi = d_inv[q];
+        if (code == LINK_PUSH) {
+            a.fout[q * plane + idx + cx * pitch + cy] = g[q];
+        } else if (code == LINK_WRAP) {
+            int64_t ty = nd.y + cy;
+            if (ty < 0) ty = L.ny - 1;
+            else if (ty >= L.ny) ty = 0;
+            a.fout[q * plane + L.at(nd.x + cx, ty)] = g[q];
+        } else if (code == LINK_SOLID_BB) {
+            // cpu/streaming_kernels.py:40-47 (k_inv = q, ind_nb = target)
+            const int64_t t = idx + cx * pitch + cy;
+            const double temp = 2 * a.p.w[q] * m.rho * a.p.inv_cs_2 *
+                                (double(cx) * a.ux[t] + double(cy) * a.uy[t]);
+            a.fout[qi * plane + idx] = g[q] - temp;
+        } else if (code == LINK_ZERO) {
+            // pulled from a ghost node that nothing ever fills
+            a.fout[qi * plane + idx] = 0.0;
+        } else if (code >= LINK_ELEMENT0) {
+            const ElementDev e = elements[code - LINK_ELEMENT0];
+            if (e.type == 0) {
+                // bounce_back, cpu/fluid_boundary_kernels.py:21-25
+                a.fout[qi * plane + idx] = g[q];
+            } else if (e.type == 1) {
+                // fixed_velocity_density_based, :51-62
+                const double temp = 2 * a.p.w[q] * m.rho * a.p.inv_cs_2 *
+                                    (double(cx) * e.v0 + double(cy) * e.v1);
+                a.fout[qi * plane + idx] = g[q] - temp;
+            } else {
+                // fixed_pressure_density_based, :126-152
+                double unx, uny;
+                node_velocity(a, L.at(nd.x + e.normal_x, nd.y + e.normal_y),
+                              unx, uny);
+                const double ex = m.ux + 0.5 * (m.ux - unx);
+                const double ey = m.uy + 0.5 * (m.uy - uny);
+                const double u2 = ex * ex + ey * ey;
+                const double cu = double(cx) * ex + double(cy) * ey;
+                const double temp = 2 * a.p.w[q] * e.scalar *
+                                    (1 + 0.5 * a.p.inv_cs_4 * cu * cu -
+                                     0.5 * a.p.inv_cs_2 * u2);
+                a.fout[qi * plane + idx] = -g[q] + temp;
+            }
+        }
+        // LINK_ZG: written by k_zero_gradient afterwards
+    }
+}
+
+// zero_gradient (our definition, see oracle/plb_oracle.c bc_zero_gradient)
+__global__ void k_zero_gradient(double *fout, int64_t plane,
+                                const ZgLink *__restrict__ links, int64_t n)
+{
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ZgLink l = links[i];
+    fout[l.v * plane + l.dst] = fout[l.v * plane + l.src];
+}
+
+// Delivery of the three populations that crossed a slab face (or the
+// periodic-x seam) into the first / last interior column.
+__global__ void k_face_unpack(Layout L, double *fout, int64_t x_col, int32_t k0,
+                              int32_t k1, int32_t k2,
+                              const double *__restrict__ src, int64_t s0,
+                              int64_t s1, int64_t s2,
+                              const uint8_t *__restrict__ mask)
+{
+    const int64_t y = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (y >= L.ny) return;
+    const uint8_t mk = mask[y];
+    const int64_t idx = L.at(x_col, y);
+    if (mk & 1) fout[k0 * L.plane + idx] = src[s0 + y];
+    if (mk & 2) fout[k1 * L.plane + idx] = src[s1 + y];
+    if (mk & 4) fout[k2 * L.plane + idx] = src[s2 + y];
+}
+
+// ---------------------------------------------------------------------------
+// initialisation: f = feq(rho, u) on fluid nodes, 0 elsewhere
+// cpu/equilibrium_kernels.py:38-78
+// ---------------------------------------------------------------------------
+__global__ void k_init_pop(KParams p, double *f, const uint8_t *__restrict__ code,
+                           const double *__restrict__ rho,
+                           const double *__restrict__ ux,
+                           const double *__restrict__ uy)
+{
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= p.L.plane) return;
+    const uint8_t c = code[i];
+    double e[Q];
+    if (c == NODE_BULK || c == NODE_LINK) {
+        Moments m;
+        m.rho = rho[i];
+        m.ux = ux[i];
+        m.uy = uy[i];
+        m.fx = m.fy = 0.0;
+        feq_all(p, m, m.ux * m.ux + m.uy * m.uy, e);
+    } else {
+#pragma unroll
+        for (int k = 0; k < Q; ++k) e[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < Q; ++k) f[k * p.L.plane + i] = e[k];
+}
+
+// ---------------------------------------------------------------------------
+// reference layout (padded, array of structures) <-> device planes
+// ---------------------------------------------------------------------------
+__global__ void k_unpack_rows(Layout L, const double *__restrict__ staging,
+                              int ncomp, double *planes, int64_t plane_stride,
+                              int64_t row0, int64_t nrows)
+{
+    const int64_t nyp = L.ny + 2;
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nrows * nyp) return;
+    const int64_t r = i / nyp, yy = i - r * nyp;
+    const int64_t d = (row0 + r) * L.pitch + L.y0 - 1 + yy;
+    for (int c = 0; c < ncomp; ++c)
+        planes[c * plane_stride + d] = staging[i * ncomp + c];
+}
+
+// zero_mode 1: entries on the ghost ring are reported as 0 (the reference
+// never writes pop_fluid_new there; our ghost columns are face staging).
+__global__ void k_pack_rows(Layout L, double *staging, int ncomp,
+                            const double *__restrict__ planes,
+                            int64_t plane_stride, int64_t row0, int64_t nrows,
+                            int zero_mode)
+{
+    const int64_t nyp = L.ny + 2;
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nrows * nyp) return;
+    const int64_t r = i / nyp, yy = i - r * nyp;
+    const int64_t row = row0 + r;
+    const int64_t d = row * L.pitch + L.y0 - 1 + yy;
+    const bool ring = row == 0 || row == L.nx + 1 || yy == 0 || yy == nyp - 1;
+    for (int c = 0; c < ncomp; ++c)
+        staging[i * ncomp + c] =
+            (zero_mode && ring) ? 0.0 : planes[c * plane_stride + d];
+}
+
+__global__ void k_pack_inner(Layout L, double *staging, int ncomp,
+                             const double *__restrict__ planes,
+                             int64_t plane_stride, int64_t x0, int64_t nrows)
+{
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nrows * L.ny) return;
+    const int64_t r = i / L.ny, y = i - r * L.ny;
+    const int64_t d = L.at(x0 + r, y);
+    for (int c = 0; c < ncomp; ++c)
+        staging[i * ncomp + c] = planes[c * plane_stride + d];
+}
+
+// ---------------------------------------------------------------------------
+// residues, cpu/compute_residues_kernels.py:6-73 (deterministic two-stage sum)
+// ---------------------------------------------------------------------------
+constexpr int RES_THREADS = 256;
+
+__global__ void __launch_bounds__(RES_THREADS)
+k_residue_partial(Layout L, const uint8_t *__restrict__ code,
+                  const double *__restrict__ rho, const double *__restrict__ ux,
+                  const double *__restrict__ uy, double *rho_old, double *ux_old,
+                  double *uy_old, double *partials)
+{
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+         i < L.plane; i += stride) {
+        const uint8_t c = code[i];
+        if (c == NODE_BULK || c == NODE_LINK) {
+            const double r = rho[i], ro = rho_old[i];
+            const double x = ux[i], xo = ux_old[i];
+            const double y = uy[i], yo = uy_old[i];
+            acc[0] += (r - ro) * (r - ro);
+            acc[1] += ro * ro;
+            acc[2] += (x - xo) * (x - xo);
+            acc[3] += xo * xo;
+            acc[4] += (y - yo) * (y - yo);
+            acc[5] += yo * yo;
+            rho_old[i] = r;
+            ux_old[i] = x;
+            uy_old[i] = y;
+        }
+    }
+    __shared__ double sh[6][RES_THREADS];
+    for (int j = 0; j < 6; ++j) sh[j][threadIdx.x] = acc[j];
+    __syncthreads();
+    for (int s = RES_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int j = 0; j < 6; ++j)
+                sh[j][threadIdx.x] += sh[j][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < 6) partials[blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+__global__ void k_residue_final(const double *__restrict__ partials, int n_blocks,
+                                double *out6)
+{
+    if (threadIdx.x < 6) {
+        double s = 0.0;
+        for (int b = 0; b < n_blocks; ++b) s += partials[b * 6 + threadIdx.x];
+        out6[threadIdx.x] = s;
+    }
+}
+
+__global__ void k_fill(double *buf, int64_t n, double value)
+{
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += stride)
+        buf[i] = value;
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+template <template <int, int, bool> class Launcher, typename... Args>
+static void dispatch(int collision, int forcing, bool store, Args &&...args)
+{
+#define PLB_CASE(C, F)                                                        \
+    if (collision == C && forcing == F) {                                     \
+        if (store) Launcher<C, F, true>::run(args...);                        \
+        else Launcher<C, F, false>::run(args...);                             \
+        return;                                                               \
+    }
+    PLB_CASE(0, 0) PLB_CASE(0, 1) PLB_CASE(0, 2)
+    PLB_CASE(1, 0) PLB_CASE(1, 1) PLB_CASE(1, 2)
+#undef PLB_CASE
+}
+
+template <int C, int F, bool S>
+struct BulkScalar {
+    static void run(const StepArgs &a, int64_t x_begin, int64_t n_rows,
+                    cudaStream_t st)
+    {
+        const int32_t chunks = int32_t((a.p.L.ny + 255) / 256);
+        k_bulk_scalar<C, F, S><<<unsigned(n_rows * chunks), 256, 0, st>>>(
+            a, x_begin, chunks);
+    }
+};
+
+template <int C, int F, bool S>
+struct BulkVec2 {
+    static void run(const StepArgs &a, int64_t x_begin, int64_t n_rows,
+                    cudaStream_t st)
+    {
+        const int32_t chunks = int32_t((a.p.L.ny + 255) / 256);
+        k_bulk_vec2<C, F, S><<<unsigned(n_rows * chunks), 128, 0, st>>>(
+            a, x_begin, chunks);
+    }
+};
+
+template <int C, int F, bool S>
+struct Links {
+    static void run(const StepArgs &a, const LinkNode *nodes, int64_t n,
+                    const ElementDev *el, cudaStream_t st)
+    {
+        k_links<C, F, S><<<unsigned((n + 127) / 128), 128, 0, st>>>(a, nodes, n,
+                                                                    el);
+    }
+};
+
+int launch_bulk(const StepArgs &a, int64_t x_begin, int64_t x_end, int variant,
+                cudaStream_t stream)
+{
+    const int64_t n_rows = x_end - x_begin;
+    if (n_rows <= 0) return 0;
+    if (variant == 0)
+        dispatch<BulkScalar>(a.collision, a.forcing, a.store != 0, a, x_begin,
+                             n_rows, stream);
+    else
+        dispatch<BulkVec2>(a.collision, a.forcing, a.store != 0, a, x_begin,
+                           n_rows, stream);
+    return 1;
+}
+
+int launch_links(const StepArgs &a, const LinkNode *nodes, int64_t n_nodes,
+                 const ElementDev *elements, cudaStream_t stream)
+{
+    if (n_nodes <= 0) return 0;
+    dispatch<Links>(a.collision, a.forcing, a.store != 0, a, nodes, n_nodes,
+                    elements, stream);
+    return 1;
+}
+
+int launch_zero_gradient(double *fout, int64_t plane, const ZgLink *links,
+                         int64_t n_links, cudaStream_t stream)
+{
+    if (n_links <= 0) return 0;
+    k_zero_gradient<<<unsigned((n_links + 127) / 128), 128, 0, stream>>>(
+        fout, plane, links, n_links);
+    return 1;
+}
+
+int launch_face_unpack(const Layout &L, double *fout, int64_t x_col,
+                       const int32_t dirs[3], const double *src,
+                       int64_t src_stride0, int64_t src_stride1,
+                       int64_t src_stride2, const uint8_t *mask,
+                       cudaStream_t stream)
+{
+    k_face_unpack<<<unsigned((L.ny + 255) / 256), 256, 0, stream>>>(
+        L, fout, x_col, dirs[0], dirs[1], dirs[2], src, src_stride0,
+        src_stride1, src_stride2, mask);
+    return 1;
+}
+
+int launch_init_pop(const KParams &p, double *f, const uint8_t *code,
+                    const double *rho, const double *ux, const double *uy,
+                    cudaStream_t stream)
+{
+    k_init_pop<<<unsigned((p.L.plane + 255) / 256), 256, 0, stream>>>(
+        p, f, code, rho, ux, uy);
+    return 1;
+}
+
+int launch_unpack_rows(const Layout &L, const double *staging, int ncomp,
+                       double *planes, int64_t plane_stride, int64_t row0,
+                       int64_t nrows, cudaStream_t stream)
+{
+    const int64_t n = nrows * (L.ny + 2);
+    k_unpack_rows<<<unsigned((n + 255) / 256), 256, 0, stream>>>(
+        L, staging, ncomp, planes, plane_stride, row0, nrows);
+    return 1;
+}
+
+int launch_pack_rows(const Layout &L, double *staging, int ncomp,
+                     const double *planes, int64_t plane_stride, int64_t row0,
+                     int64_t nrows, const uint8_t *, int zero_mode,
+                     cudaStream_t stream)
+{
+    const int64_t n = nrows * (L.ny + 2);
+    k_pack_rows<<<unsigned((n + 255) / 256), 256, 0, stream>>>(
+        L, staging, ncomp, planes, plane_stride, row0, nrows, zero_mode);
+    return 1;
+}
+
+int launch_pack_inner(const Layout &L, double *staging, int ncomp,
+                      const double *planes, int64_t plane_stride, int64_t x0,
+                      int64_t nrows, cudaStream_t stream)
+{
+    const int64_t n = nrows * L.ny;
+    k_pack_inner<<<unsigned((n + 255) / 256), 256, 0, stream>>>(
+        L, staging, ncomp, planes, plane_stride, x0, nrows);
+    return 1;
+}
+
+int launch_residue(const Layout &L, const uint8_t *code, const double *rho,
+                   const double *ux, const double *uy, double *rho_old,
+                   double *ux_old, double *uy_old, double *partials,
+                   int n_blocks, double *out6, cudaStream_t stream)
+{
+    k_residue_partial<<<n_blocks, RES_THREADS, 0, stream>>>(
+        L, code, rho, ux, uy, rho_old, ux_old, uy_old, partials);
+    k_residue_final<<<1, 32, 0, stream>>>(partials, n_blocks, out6);
+    return 2;
+}
+
+int launch_fill(double *buf, int64_t n, double value, cudaStream_t stream)
+{
+    k_fill<<<148 * 8, 256, 0, stream>>>(buf, n, value);
+    return 1;
+}
+
+}  // namespace plb

@@ -1,0 +1,230 @@
+"""The fluidLB solver on the b200 back end: mirror of
+pylabolt/solvers/fluidLB.py (Solver :108-395, main :398-407).
+
+Same life cycle -- ``Solver(comm, backend, n_threads)``, ``set_backend()``,
+``compile()``, ``run()`` -- and the same seam: ``execute_single_time_step`` is
+a zero-argument callable bound in ``compile()`` (reference :273-280) and
+called once per step by ``run()`` (:356).  In the reference that callable runs
+nine operator calls and five full-lattice numba kernels; here it is one call
+into libplb (``plb_step``), which fuses phases 2-8 into a single pass over HBM.
+
+There is no CPU path: without the CUDA library or a CUDA device the solver
+raises.
+"""
+import os
+import time
+
+import numpy as np
+
+from . import capi
+from .helpers import SimulationStatusLogger, load_simulation, print_log
+from .io_operator import InputOutputOperator
+from .operators import CollisionOperator, FluidLB, ForceOperator
+from .residues import ResidueOperator
+from .state import State
+
+__version__ = "1.0.0.dev0+b200"
+
+
+class Backend:
+    """Hardware back end descriptor (pylabolt/parallel/backend.py:18-81).
+    The only back end of this package is ``b200``: one process per GPU."""
+
+    def __init__(self, comm, state, backend="b200", n_threads=1, device=None,
+                 strict=None, verbose=True):
+        rank = state.domain.mpi_rank
+        if backend not in ("b200", "gpu"):
+            print_log("-" * 80, rank, True)
+            print_log("FATAL ERROR!", rank, True)
+            print_log("pylabolt_b200 has no '" + str(backend) + "' back end; "
+                      "use --backend b200", rank, True)
+            comm.Abort()
+            raise ValueError("unsupported backend: " + str(backend))
+        self.backend_type = "b200"
+        self.no_of_threads = n_threads
+        self.strict = strict
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = device
+        capi.load_library(strict)      # fail loudly now, not at the first step
+        print_log(f"{'Backend':<25}: b200 (sm_100a, libplb)", rank, verbose)
+        print_log(f"{'CUDA device':<25}: {self.device}", rank, verbose)
+
+
+def neighbour_ranks(domain, boundary):
+    """MPIOperator.find_neighbor_ranks (parallel/MPI_operator.py:116-153) for
+    x-slabs: (left_rank, right_rank), None where the slab ends at a
+    non-periodic domain edge."""
+    n = domain.no_of_procs_x
+    i = domain.i_proc
+    left = None if (i == 0 and not boundary.x_periodic) else (i - 1 + n) % n
+    right = None if (i == n - 1 and not boundary.x_periodic) else (i + 1) % n
+    return left, right
+
+
+class Solver:
+    def __init__(self, comm, backend="b200", n_threads=1, simulation=None,
+                 device=None, strict=None, verbose=True):
+        mpi_rank = comm.Get_rank()
+        self.comm = comm
+        self.verbose = verbose
+        print_log(f"\n{'PyLaBolt':<10}: {__version__}", mpi_rank, verbose)
+        print_log(f"{'Solver':<10}: fluidLB", mpi_rank, verbose)
+        self.model = FluidLB()
+        if simulation is None:
+            simulation = load_simulation(comm, mpi_rank)
+        self.simulation = simulation
+        self.state = State(simulation, comm, mpi_rank, fluid=True,
+                           verbose=verbose)
+        self.backend = Backend(comm, self.state, backend, n_threads,
+                               device=device, strict=strict, verbose=verbose)
+        self.collision_operator = CollisionOperator(
+            simulation, self.model, self.state, comm, verbose=verbose)
+        self.force_operator = ForceOperator(
+            simulation, self.model, self.state, comm,
+            collision_operator=self.collision_operator, verbose=verbose)
+        try:
+            self.state.obstacle.check_overlap(comm)
+        except RuntimeError as e:
+            print_log(str(e), mpi_rank, True)
+            comm.Abort()
+            raise
+        self.residue_operator = ResidueOperator(self.model, self.state, comm,
+                                                verbose=verbose)
+        self.io_operator = InputOutputOperator(self.model, self.state,
+                                               self.backend, comm,
+                                               verbose=verbose)
+        self.logger = SimulationStatusLogger(mpi_rank, verbose=verbose)
+        self.plb = None
+        self.time_step = self.state.control.start_time
+        self.execute_single_time_step = None
+
+    # -- reference: Solver.set_backend, fluidLB.py:186-204 ---------------------
+    def set_backend(self, verbose=None):
+        verbose = self.verbose if verbose is None else verbose
+        st = self.state
+        rank = st.domain.mpi_rank
+        print_log("-" * 80, rank, verbose)
+        print_log("Setting simulation backend...\n", rank, verbose)
+        left, right = neighbour_ranks(st.domain, st.boundary)
+        self.left_rank, self.right_rank = left, right
+        col = self.collision_operator
+        self.plb = capi.Plb(
+            st.domain.Nx_rank, st.domain.Ny_rank, col.omega_fluid,
+            device=self.backend.device, collision=col.collision_fluid,
+            forcing=col.forcing_fluid, gravity=self.force_operator.gravity,
+            x_periodic=st.boundary.x_periodic,
+            y_periodic=st.boundary.y_periodic,
+            left_neighbor=left is not None, right_neighbor=right is not None,
+            mrt_rates=col.mrt_rates,
+            lattice={"inv_cs_2": st.lattice.inv_cs_2,
+                     "inv_cs_4": st.lattice.inv_cs_4,
+                     "weights": st.lattice.weights},
+            float_min=st.control.float_min, strict=self.backend.strict)
+        plb = self.plb
+        plb.upload(capi.SOLID, st.fields.solid)
+        plb.upload(capi.DENSITY, st.fields.density)
+        plb.upload(capi.VELOCITY, st.fields.velocity)
+        for element in st.boundary.boundary_elements:
+            plb.add_boundary_element(
+                element.type_fluid, element.boundary_nodes, element.out_list,
+                element.inv_list, element.normal, element.vector_fluid,
+                element.scalar_fluid)
+        plb.finalize_geometry()
+        if st.domain.mpi_size > 1:
+            unique_id = plb.comm_unique_id() if rank == 0 else bytes(128)
+            unique_id = self.comm.bcast_bytes(unique_id, root=0)
+            plb.comm_init(unique_id, rank, st.domain.mpi_size,
+                          -1 if left is None else left,
+                          -1 if right is None else right)
+        self.residue_operator.set_backend(st, self.backend, plb)
+        self.io_operator.set_backend(st, self.backend, plb)
+        print_log("\nSetting simulation backend done!", rank, verbose)
+        print_log("-" * 80, rank, verbose)
+
+    # -- reference: Solver.single_time_step, fluidLB.py:206-253 ----------------
+    def single_time_step(self, store_moments=False):
+        """One reference time step: phases 2-8 (moments, gravity force,
+        collision, halo exchange, streaming with in-flight bounce back,
+        boundary elements) as one fused pass inside libplb.  With
+        ``store_moments`` the step also leaves rho / u (phases 2-4) in HBM for
+        output and residues, which the reference does on every step."""
+        self.plb.step(1, store_moments)
+
+    def advance(self, n_steps, store_moments_last=False):
+        """``n_steps`` calls of single_time_step in one library call."""
+        self.plb.step(n_steps, store_moments_last)
+
+    # -- reference: Solver.compile, fluidLB.py:255-284 -------------------------
+    def compile(self, verbose=None):
+        """Nothing is JIT-compiled: libplb is built ahead of time for sm_100a.
+        Binds the step slot, like the reference binds it to its CUDA graph."""
+        verbose = self.verbose if verbose is None else verbose
+        if self.plb is None:
+            raise RuntimeError("set_backend() must be called before compile()")
+        self.execute_single_time_step = self.single_time_step
+        print_log("Step slot bound to libplb (plb_step)",
+                  self.state.domain.mpi_rank, verbose)
+
+    def _needs_moments(self, time_step):
+        c = self.state.control
+        return ((c.std_out_interval is not None and
+                 time_step % c.std_out_interval == 0) or
+                (c.save_interval is not None and
+                 time_step % c.save_interval == 0))
+
+    # -- reference: Solver.run, fluidLB.py:309-395 ------------------------------
+    def run(self, verbose=None):
+        verbose = self.verbose if verbose is None else verbose
+        st = self.state
+        rank = st.domain.mpi_rank
+        print_log("\n" + "-" * 80, rank, verbose)
+        print_log("Running simulation...\n", rank, verbose)
+        self.plb.initialize_pop()
+        self.io_operator.write_fields(st, self.backend, st.control.start_time)
+        run_time_start = time.perf_counter()
+        for time_step in range(st.control.start_time + 1,
+                               st.control.end_time + 1):
+            if self._needs_moments(time_step):
+                self.single_time_step(store_moments=True)
+            else:
+                self.execute_single_time_step()
+            self.time_step = time_step
+            self.residue_operator.compute_residues(st, self.backend, self.comm,
+                                                   time_step)
+            self.logger.log_data(
+                st, time_step,
+                res_density=self.residue_operator.residues["res_density"],
+                res_velocity=self.residue_operator.residues["res_velocity"])
+            self.io_operator.write_fields(st, self.backend, time_step)
+        self.plb.sync()
+        run_time = time.perf_counter() - run_time_start
+        print_log("\n" + "-" * 80, rank, verbose)
+        print_log(f"{'Simulation complete, run time':<30}: "
+                  f"{str(run_time) + ' s':<30}", rank, verbose)
+        print_log("-" * 80, rank, verbose)
+        return run_time
+
+    # -- host views of device fields (parity tests, post-processing) ------------
+    def fields_to_host(self):
+        """density, velocity and pop_fluid_new in the reference's padded
+        layouts, as numpy arrays."""
+        return {"density": self.plb.download(capi.DENSITY),
+                "velocity": self.plb.download(capi.VELOCITY),
+                "pop_fluid_new": self.plb.download(capi.POP)}
+
+    def close(self):
+        if self.plb is not None:
+            self.plb.close()
+            self.plb = None
+
+
+def main(backend="b200", n_threads=1, debug_mode=False):
+    """pylabolt/solvers/fluidLB.py:398-407."""
+    from .comm import world_comm
+    comm = world_comm()
+    solver = Solver(comm, backend, n_threads)
+    solver.set_backend()
+    solver.compile()
+    solver.run()
+    solver.close()
