@@ -1,0 +1,484 @@
+#!/usr/bin/env python
+"""bench.py -- fluidLB time-step throughput (D2Q9, fp64) in GLUPS.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload channel|cavity]
+                    [--impl reference]
+
+Workload (BASELINE.json configs[4], the weak-scaling case the metric's
+multi-GPU target is quoted on): periodic channel, 8192 x 16384 lattice nodes
+per GPU (Nx = 8192 * N), MRT + Guo second-order forcing, gravity [1e-6, 0],
+bounce_back plates top / bottom, x-periodic across the slabs, rho = 1 and a
+seeded velocity perturbation.  `--workload cavity` runs configs[3] instead
+(16384 x 16384 lid-driven cavity, BGK, strong scaling) and, at N = 1, the
+default run reports it too under "extra".
+
+One "step" = one reference time step (Solver.single_time_step) of the whole
+lattice.  value = lattice-node updates of all ranks / max-over-ranks device
+time, populations resident in HBM.  e2e = the same through the public Solver
+API with host buffers: upload of the initial rho / u from pinned host memory,
+initialisation, K steps issued one by one from Python through the
+execute_single_time_step slot, the residue read-back and the download of
+rho / u into pinned host memory, all inside the timed region.
+
+The lattice (19.3 GB of populations per GPU) is far larger than L2, so no L2
+flush is needed between steps (config.l2 says so).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for _p in (REPO, os.path.join(REPO, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+ALGORITHMIC_BYTES_PER_NODE = 144          # 9 x 8 B read + 9 x 8 B write
+HBM_FALLBACK_GBS = 6650.0                 # B200_PROFILING.md fallback
+
+
+# --------------------------------------------------------------------------
+# workloads (reference case-file schema)
+# --------------------------------------------------------------------------
+def hash_noise(i, j, salt):
+    """Deterministic, rank-independent pseudo-random field in [-0.5, 0.5)."""
+    t = np.sin(i * 12.9898 + j * 78.233 + salt) * 43758.5453
+    return t - np.floor(t) - 0.5
+
+
+def perturbed_velocity(amplitude):
+    def func(i, j):
+        i = np.asarray(i, dtype=np.float64)
+        j = np.asarray(j, dtype=np.float64)
+        return (amplitude * hash_noise(i, j, 0.0),
+                amplitude * hash_noise(i, j, 17.0))
+    func.vectorized = True
+    return func
+
+
+def channel_case(nx, ny, n_ranks, steps):
+    """BASELINE.json configs[4]."""
+    from types import SimpleNamespace
+    return SimpleNamespace(
+        control_dict={"start_time": 0, "end_time": steps,
+                      "std_out_interval": steps, "save_interval": steps,
+                      "checkpoint_interval": None, "precision": "double"},
+        mesh_dict={"grid": [nx, ny]},
+        lattice_dict={"lattice_type": "D2Q9"},
+        decompose_dict={"nx": n_ranks, "ny": 1},
+        transport_dict={"kin_visc": 0.1},
+        initial_fields_dict={"default": {"fluid": {
+            "velocity": {"type": "func", "func": perturbed_velocity(0.01)},
+            "density": {"type": "fixed", "value": 1.0},
+            "pressure": {"type": "fixed", "value": 0.0}}}},
+        boundary_dict={
+            "options": {},
+            "inout": {"wall": False,
+                      "segments": [[[0, 0], [0, ny - 1]],
+                                   [[nx - 1, 0], [nx - 1, ny - 1]]],
+                      "fluid": {"type": "periodic"}},
+            "plates": {"wall": True,
+                       "segments": [[[0, 0], [nx - 1, 0]],
+                                    [[0, ny - 1], [nx - 1, ny - 1]]],
+                       "fluid": {"type": "bounce_back"}}},
+        obstacle_dict={"options": {}},
+        collision_dict={"fluid": {"model": "MRT",
+                                  "equilibrium": "density_based_second_order",
+                                  "forcing_model": "guo_second_order"}},
+        forcing_dict={"gravity": [1.0e-6, 0.0]})
+
+
+def cavity_case(nx, ny, n_ranks, steps):
+    """BASELINE.json configs[3]."""
+    import cases
+    sim = cases.cavity(nx, ny, end_time=steps)
+    sim.control_dict["std_out_interval"] = steps
+    sim.control_dict["save_interval"] = steps
+    sim.decompose_dict = {"nx": n_ranks, "ny": 1}
+    sim.initial_fields_dict["default"]["fluid"]["velocity"] = {
+        "type": "func", "func": perturbed_velocity(0.01)}
+    return sim
+
+
+WORKLOADS = {
+    # name: (factory, per-GPU nx (weak) or total nx (strong), ny, scaling, text)
+    "channel": (channel_case, 8192, 16384, "weak",
+                "periodic channel {nx}x{ny} ({per}x{ny} per GPU), fp64 MRT + "
+                "Guo second-order forcing, x-periodic slabs, bounce_back plates"),
+    "cavity": (cavity_case, 16384, 16384, "strong",
+               "lid-driven cavity {nx}x{ny}, fp64 BGK, halfway bounce-back + "
+               "moving wall"),
+}
+
+
+def workload_sizes(name, n_ranks, scale):
+    factory, nx, ny, scaling, text = WORKLOADS[name]
+    nx = max(n_ranks, int(nx * scale))
+    ny = max(8, int(ny * scale))
+    total_nx = nx * n_ranks if scaling == "weak" else nx
+    per = total_nx // n_ranks
+    return factory, total_nx, ny, scaling, text.format(nx=total_nx, ny=ny,
+                                                       per=per)
+
+
+# --------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,"
+             "clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device),
+                 "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.out, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.close()
+        sm, sm_max, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 8:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    sm_max.append(float(parts[2]))
+                    power.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for name, flag in zip(names, parts[4:8]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(sm_max)),
+                "power_w_max": float(max(power)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def hbm_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """Per-launch DRAM bytes of the bulk kernel from the committed ncu
+    capture (profiles/ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+def make_oracle(sim, n_threads):
+    """CPU oracle on the same case, built from our own host-side State."""
+    from oracle.oracle import Oracle
+    from pylabolt_b200.comm import SingleComm
+    from pylabolt_b200.operators import CollisionOperator, FluidLB, ForceOperator
+    from pylabolt_b200.state import State
+    comm = SingleComm()
+    st = State(sim, comm, 0, verbose=False)
+    col = CollisionOperator(sim, FluidLB(), st, comm, verbose=False)
+    frc = ForceOperator(sim, FluidLB(), st, comm, collision_operator=col,
+                        verbose=False)
+    elements = [{"type": el.type_fluid, "nodes": el.boundary_nodes,
+                 "out": el.out_list, "inv": el.inv_list, "normal": el.normal,
+                 "vector": el.vector_fluid, "scalar": float(el.scalar_fluid)}
+                for el in st.boundary.boundary_elements]
+    orc = Oracle(st.domain.shape, st.fields.solid, st.fields.ghost_node,
+                 st.fields.density, st.fields.velocity, elements,
+                 col.omega_fluid, gravity=frc.gravity, forcing=col.forcing_fluid,
+                 collision=col.collision_fluid,
+                 x_periodic=st.boundary.x_periodic,
+                 y_periodic=st.boundary.y_periodic, mrt_rates=col.mrt_rates,
+                 n_threads=n_threads)
+    orc.initialize_pop()
+    return orc, int(st.domain.inner_size)
+
+
+def time_cpu_port(workload, steps, warmup, budget_s=12.0, sample=2048):
+    """The oracle (CPU port of the reference's five-pass step, OpenMP where
+    the reference has numba prange) on a bounded sample of the workload."""
+    factory = WORKLOADS[workload][0]
+    cores = os.cpu_count() or 1
+    sim = factory(sample, sample, 1, 1)
+    orc, nodes = make_oracle(sim, cores)
+    for _ in range(max(1, warmup)):
+        orc.step(1)
+    t0 = time.perf_counter()
+    orc.step(1)
+    one = time.perf_counter() - t0
+    per_step = []
+    n = max(1, steps)
+    deadline = time.perf_counter() + budget_s
+    for _ in range(n):
+        t0 = time.perf_counter()
+        orc.step(1)
+        per_step.append(time.perf_counter() - t0)
+        if time.perf_counter() > deadline:
+            break
+    mean = float(np.mean(per_step)) if per_step else one
+    return {"value": nodes / mean / 1e9, "unit": "GLUPS", "cores": cores,
+            "kind": "port",
+            "sample": f"{sample}x{sample} nodes of the same case, "
+                      f"{len(per_step)} timed steps, {cores} OpenMP threads "
+                      "(oracle/plb_oracle.c, five-pass AoS like the reference)",
+            "ms_per_step": mean * 1e3, "steps": len(per_step)}
+
+
+# --------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------
+def run_reference(args, rank, world, text, scaling):
+    if rank != 0:
+        return
+    base = time_cpu_port(args.workload, args.steps, args.warmup,
+                         budget_s=90.0, sample=4096)
+    line = {
+        "impl": "reference", "metric": "fluidLB D2Q9 fp64 lattice updates",
+        "value": base["value"], "unit": "GLUPS", "n_gpus": args.gpus,
+        "steps": base["steps"], "warmup": args.warmup,
+        "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": text,
+                   "note": "reference's CPU path (oracle port: the reference "
+                           "is Python/numba and cannot travel to the GPU box)"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind",
+                                              "sample")},
+        "e2e": {"value": base["value"], "unit": "GLUPS",
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def measure(workload, comm, rank, world, steps, warmup, scale, device):
+    from pylabolt_b200 import capi
+    from pylabolt_b200.solver import Solver
+
+    factory, nx, ny, scaling, text = workload_sizes(workload, world, scale)
+    sim = factory(nx, ny, world, steps)
+    solver = Solver(comm, "b200", simulation=sim, device=device, verbose=False)
+    st = solver.state
+    total_nodes = nx * ny
+    solver.set_backend()
+    solver.compile()
+    plb = solver.plb
+    info = plb.info()
+
+    # ---- device-resident throughput -------------------------------------
+    plb.initialize_pop()
+    plb.step(warmup, False)
+    plb.sync()
+    comm.Barrier()
+    sampler = ClockSampler(device)
+    sampler.start()
+    plb.kernel_launches(reset=True)
+    plb.profile_enable(True)
+    plb.sync()
+    comm.Barrier()
+    plb.event_record(0)
+    plb.step(steps, False)
+    plb.event_record(1)
+    plb.sync()
+    comm.Barrier()
+    ms = plb.event_elapsed_ms(0, 1)
+    launches = plb.kernel_launches()
+    bulk_ms, bulk_n = plb.profile_read()
+    plb.profile_enable(False)
+    clocks = sampler.stop()
+    t = np.array([ms], dtype=np.float64)
+    t_max = np.zeros_like(t)
+    comm.Allreduce(t, t_max, op="max")
+    ms = float(t_max[0])
+    value = total_nodes * steps / (ms * 1e-3) / 1e9
+
+    # roofline of the dominant kernel (bulk collide-stream), this rank
+    peak, peak_src = hbm_peak()
+    bulk_ms_per_step = bulk_ms / steps
+    achieved = (ALGORITHMIC_BYTES_PER_NODE * info["n_bulk"] /
+                (bulk_ms_per_step * 1e-3) / 1e9)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(workload),
+                "kernel": "k_bulk_vec2" if info["variant"] else "k_bulk_scalar",
+                "algorithmic_bytes_per_step":
+                    ALGORITHMIC_BYTES_PER_NODE * info["n_bulk"],
+                "launches_per_step": bulk_n / steps,
+                "kernel_ms_per_step": bulk_ms_per_step,
+                "kernel_share_of_step": bulk_ms / (ms * 1.0),
+                "peak_source": peak_src}
+
+    # ---- end to end through the public Solver API, host buffers -----------
+    size = plb.size
+    rho_in = plb.pinned((size,))
+    u_in = plb.pinned((size, 2))
+    rho_out = plb.pinned((plb.nx * plb.ny,))
+    u_out = plb.pinned((plb.nx * plb.ny, 2))
+    rho_in.array[:] = st.fields.density
+    u_in.array[:] = st.fields.velocity
+    plb.sync()
+    comm.Barrier()
+    t0 = time.perf_counter()
+    plb.event_record(2)
+    plb.upload(capi.DENSITY, rho_in.array)
+    plb.upload(capi.VELOCITY, u_in.array)
+    plb.initialize_pop()
+    for _ in range(steps - 1):
+        solver.execute_single_time_step()
+    solver.single_time_step(store_moments=True)
+    solver.residue_operator.compute_residues(st, solver.backend, comm, steps)
+    plb.download(capi.DENSITY_INNER, rho_out.array)
+    plb.download(capi.VELOCITY_INNER, u_out.array)
+    plb.event_record(3)
+    plb.sync()
+    comm.Barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(plb.event_elapsed_ms(2, 3), 0.0)
+    t = np.array([max(e2e_ms, wall_ms)], dtype=np.float64)
+    comm.Allreduce(t, t_max, op="max")
+    e2e_ms = float(t_max[0])
+    mass = float(rho_out.array.sum())
+    h2d = (rho_in.array.nbytes + u_in.array.nbytes) * world
+    d2h = (rho_out.array.nbytes + u_out.array.nbytes + 48) * world
+    e2e = {"value": total_nodes * steps / (e2e_ms * 1e-3) / 1e9,
+           "unit": "GLUPS", "h2d_bytes_per_step": h2d / steps,
+           "d2h_bytes_per_step": d2h / steps, "ms_total": e2e_ms,
+           "steps": steps,
+           "what": "upload rho,u (pinned) + initialize_pop + K python-issued "
+                   "steps + residues + download rho,u (pinned)",
+           "mean_density_check": mass / (plb.nx * plb.ny)}
+    for buf in (rho_in, u_in, rho_out, u_out):
+        buf.free()
+    solver.close()
+    return {"value": value, "ms": ms, "launches": launches, "scaling": scaling,
+            "text": text, "roofline": roofline, "e2e": e2e, "clocks": clocks,
+            "nx": nx, "ny": ny, "info": info}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="channel", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0,
+                    help="shrink the lattice (debugging only; a scaled run is "
+                         "not a benchmark value)")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # relaunch under torchrun, one rank per GPU
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                   "--master-port", os.environ.get("MASTER_PORT", "29511"),
+                   os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    args.warmup = max(args.warmup, 3)
+
+    _, _, _, scaling, text = workload_sizes(args.workload, world, args.scale)
+    if args.impl == "reference":
+        run_reference(args, rank, world, text, scaling)
+        return
+
+    from pylabolt_b200.comm import SingleComm, TorchComm
+    comm = TorchComm() if world > 1 else SingleComm()
+    res = measure(args.workload, comm, rank, world, args.steps, args.warmup,
+                  args.scale, local_rank)
+    extra = {}
+    if world == 1 and not args.no_extras and args.workload == "channel":
+        cav = measure("cavity", comm, rank, world, max(20, args.steps // 4),
+                      args.warmup, args.scale, local_rank)
+        extra["cavity_16384_bgk"] = {
+            "value": cav["value"], "unit": "GLUPS",
+            "ms_per_step": cav["ms"] / max(20, args.steps // 4),
+            "workload": cav["text"],
+            "roofline": cav["roofline"], "e2e": cav["e2e"]}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = time_cpu_port(args.workload, 10, 2)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        line = {
+            "metric": "fluidLB D2Q9 fp64 lattice updates",
+            "value": res["value"], "unit": "GLUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms"] / args.steps, "higher_is_better": True,
+            "scaling": res["scaling"], "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": res["text"], "nx": res["nx"], "ny": res["ny"],
+                       "parallelism": f"x-slabs x{world}",
+                       "l2": "lattice (19 GB/GPU) >> L2, no flush needed",
+                       "kernel_variant": res["roofline"]["kernel"],
+                       "scale": args.scale},
+            "roofline": res["roofline"],
+            "cpu_baseline": cpu,
+            "e2e": res["e2e"],
+            "gpu_launches": res["launches"],
+            "clocks": res["clocks"],
+            "hbm_roofline_frac_whole_step":
+                res["value"] * 1e9 * ALGORITHMIC_BYTES_PER_NODE / world /
+                (res["roofline"]["peak"] * 1e9),
+        }
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

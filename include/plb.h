@@ -166,6 +166,14 @@ int plb_comm_init(plb_handle h, const void *id128, int32_t rank,
 int plb_event_record(plb_handle h, int32_t slot);
 int plb_event_elapsed_ms(plb_handle h, int32_t start_slot, int32_t stop_slot,
                          float *ms);
+/* Per-kernel timing of the dominant (bulk collide-stream) kernel: while
+ * enabled, every bulk launch is bracketed by CUDA events on the launching
+ * stream.  plb_profile_read returns the summed duration and the number of
+ * launches since the last read (it synchronises the events). */
+int plb_profile_enable(plb_handle h, int32_t enable);
+int plb_profile_read(plb_handle h, double *bulk_ms, int64_t *n_launches);
+/* out = {n_bulk, n_link, n_solid, pitch, plane, kernel_variant, 0, 0} */
+int plb_info(plb_handle h, int64_t out[8]);
 /* Kernels launched by this handle since creation / since the last reset. */
 int64_t plb_kernel_launches(plb_handle h, int32_t reset);
 /* Pinned host memory for upload / download buffers. */

@@ -29,6 +29,7 @@ EXPORTS = [
     "plb_comm_unique_id", "plb_comm_init",
     "plb_event_record", "plb_event_elapsed_ms", "plb_kernel_launches",
     "plb_host_alloc", "plb_host_free", "plb_flush_l2",
+    "plb_profile_enable", "plb_profile_read", "plb_info",
 ]
 
 
@@ -94,6 +95,10 @@ def load_library(strict=None):
     lib.plb_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     lib.plb_host_free.argtypes = [vp]
     lib.plb_flush_l2.argtypes = [vp]
+    lib.plb_profile_enable.argtypes = [vp, i32]
+    lib.plb_profile_read.argtypes = [vp, ctypes.POINTER(dbl),
+                                     ctypes.POINTER(i64)]
+    lib.plb_info.argtypes = [vp, ctypes.POINTER(i64)]
     _libs[strict] = lib
     return lib
 
@@ -271,6 +276,22 @@ class Plb:
 
     def kernel_launches(self, reset=False):
         return int(self.lib.plb_kernel_launches(self._h, int(reset)))
+
+    def profile_enable(self, enable=True):
+        self._check(self.lib.plb_profile_enable(self._h, int(bool(enable))))
+
+    def profile_read(self):
+        """(summed bulk-kernel ms, launches) since the last read."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        self._check(self.lib.plb_profile_read(self._h, ctypes.byref(ms),
+                                              ctypes.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def info(self):
+        out = (ctypes.c_int64 * 8)()
+        self._check(self.lib.plb_info(self._h, out))
+        keys = ("n_bulk", "n_link", "n_solid", "pitch", "plane", "variant")
+        return dict(zip(keys, out[:6]))
 
     def flush_l2(self):
         self._check(self.lib.plb_flush_l2(self._h))

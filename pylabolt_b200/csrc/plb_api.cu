@@ -111,6 +111,7 @@ struct plb_solver {
     Layout L;
     KParams kp;
     int variant = 1;                 // 0 scalar, 1 vec2 (env PLB_KERNEL)
+    int kernel_collision = 0;        // 0 BGK, 1 MRT (free rates), 2 MRT (reference rates)
 
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
@@ -143,6 +144,10 @@ struct plb_solver {
 
     int64_t launches = 0;
     int64_t steps_done = 0;
+
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;   // start/stop pairs
+    size_t prof_used = 0;
 
     double *rho() const { return mom; }
     double *ux() const { return mom + L.plane; }
@@ -295,6 +300,27 @@ int run_zero_gradient(plb_solver *s, double *fout, cudaStream_t st)
     return PLB_OK;
 }
 
+int bulk_timed(plb_solver *s, const StepArgs &a, int64_t x0, int64_t x1)
+{
+    if (x1 <= x0) return PLB_OK;
+    if (s->profile) {
+        if (s->prof_used + 2 > s->prof_events.size()) {
+            for (int i = 0; i < 2; ++i) {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreate(&e));
+                s->prof_events.push_back(e);
+            }
+        }
+        CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used], s->stream));
+    }
+    s->launches += launch_bulk(a, x0, x1, s->variant, s->stream);
+    if (s->profile) {
+        CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used + 1], s->stream));
+        s->prof_used += 2;
+    }
+    return PLB_OK;
+}
+
 int step_once(plb_solver *s, bool store)
 {
     const Layout &L = s->L;
@@ -306,7 +332,7 @@ int step_once(plb_solver *s, bool store)
     a.rho = s->rho();
     a.ux = s->ux();
     a.uy = s->uy();
-    a.collision = s->cfg.collision;
+    a.collision = s->kernel_collision;
     a.forcing = s->cfg.forcing;
     a.store = store ? 1 : 0;
     double *fout = a.fout;
@@ -314,7 +340,7 @@ int step_once(plb_solver *s, bool store)
     const bool faces = s->cfg.left_neighbor || s->cfg.right_neighbor;
 
     if (!s->comm) {
-        s->launches += launch_bulk(a, 0, L.nx, s->variant, s->stream);
+        if (int rc = bulk_timed(s, a, 0, L.nx)) return rc;
         s->launches += launch_links(a, s->links_dev, s->n_links, s->elements_dev,
                                     s->stream);
         if (faces) {
@@ -333,9 +359,9 @@ int step_once(plb_solver *s, bool store)
         run_zero_gradient(s, fout, s->stream);
     } else {
         // slab edges first, so that the face exchange overlaps the interior
-        s->launches += launch_bulk(a, 0, 1, s->variant, s->stream);
+        if (int rc = bulk_timed(s, a, 0, 1)) return rc;
         if (L.nx > 1)
-            s->launches += launch_bulk(a, L.nx - 1, L.nx, s->variant, s->stream);
+            if (int rc = bulk_timed(s, a, L.nx - 1, L.nx)) return rc;
         s->launches += launch_links(a, s->links_dev, s->n_links, s->elements_dev,
                                     s->stream);
         CUDA_TRY(cudaEventRecord(s->ev_edge, s->stream));
@@ -371,7 +397,7 @@ int step_once(plb_solver *s, bool store)
                                               s->recv_right, 0, L.ny, 2 * L.ny,
                                               s->mask_right, s->comm_stream);
         CUDA_TRY(cudaEventRecord(s->ev_comm, s->comm_stream));
-        s->launches += launch_bulk(a, 1, L.nx - 1, s->variant, s->stream);
+        if (int rc = bulk_timed(s, a, 1, L.nx - 1)) return rc;
         CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
         run_zero_gradient(s, fout, s->stream);
     }
@@ -434,6 +460,15 @@ int plb_create(const plb_config *c, plb_handle *out)
     }
     if (const char *v = getenv("PLB_KERNEL"))
         s->variant = (strcmp(v, "scalar") == 0) ? 0 : 1;
+    s->kernel_collision = c->collision;
+    if (c->collision == PLB_MRT) {
+        // S = (1,..,1,s7,s8) as in base/collision_operator.py:159-163 needs
+        // only the two stress moments (mrt_reduced_all)
+        bool reference_rates = true;
+        for (int k = 0; k < 7; ++k) reference_rates &= c->mrt_rates[k] == 1.0;
+        const char *g = getenv("PLB_MRT_GENERAL");
+        if (reference_rates && !(g && g[0] == '1')) s->kernel_collision = 2;
+    }
 
     auto cleanup = [&](int rc) {
         plb_destroy(s);
@@ -490,6 +525,7 @@ void plb_destroy(plb_handle s)
     cudaFree(s->recv_right);
     for (auto &e : s->events)
         if (e) cudaEventDestroy(e);
+    for (auto &e : s->prof_events) cudaEventDestroy(e);
     if (s->ev_edge) cudaEventDestroy(s->ev_edge);
     if (s->ev_comm) cudaEventDestroy(s->ev_comm);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
@@ -842,6 +878,44 @@ int plb_event_elapsed_ms(plb_handle s, int32_t a, int32_t b, float *ms)
     CUDA_TRY(cudaSetDevice(s->cfg.device));
     CUDA_TRY(cudaEventSynchronize(s->events[b]));
     CUDA_TRY(cudaEventElapsedTime(ms, s->events[a], s->events[b]));
+    return PLB_OK;
+}
+
+int plb_profile_enable(plb_handle s, int32_t enable)
+{
+    if (!s) return fail(PLB_ERR_INVALID, "null handle");
+    s->profile = enable != 0;
+    s->prof_used = 0;
+    return PLB_OK;
+}
+
+int plb_profile_read(plb_handle s, double *bulk_ms, int64_t *n_launches)
+{
+    if (!s || !bulk_ms || !n_launches) return fail(PLB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < s->prof_used; i += 2) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventSynchronize(s->prof_events[i + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms, s->prof_events[i], s->prof_events[i + 1]));
+        total += ms;
+    }
+    *bulk_ms = total;
+    *n_launches = int64_t(s->prof_used / 2);
+    s->prof_used = 0;
+    return PLB_OK;
+}
+
+int plb_info(plb_handle s, int64_t out[8])
+{
+    if (!s || !out) return fail(PLB_ERR_INVALID, "null argument");
+    out[0] = s->n_bulk;
+    out[1] = s->n_links;
+    out[2] = s->n_solid;
+    out[3] = s->L.pitch;
+    out[4] = s->L.plane;
+    out[5] = s->variant;
+    out[6] = out[7] = 0;
     return PLB_OK;
 }
 

@@ -217,7 +217,109 @@ __device__ __forceinline__ void mrt_all(const KParams &p, const Moments &m,
     for (int k = 0; k < Q; ++k) g[k] = f[k] + dv[k];
 }
 
+// Guo source for the MRT paths.  MRT has no upstream arithmetic to preserve,
+// so the second-order bracket is evaluated in the cheaper, algebraically
+// identical form  w_k * (inv_cs_2 * (c_k.F - u.F) + inv_cs_4 * (c_k.u)(c_k.F)).
+template <int K, int FORCING>
+__device__ __forceinline__ double guo_mrt(const KParams &p, const Moments &m,
+                                          double uF)
+{
+    if constexpr (FORCING == 1) {
+        return guo<K, 1>(p, m);
+    } else if constexpr (K == 0) {
+        return -(p.w[0] * p.inv_cs_2) * uF;
+    } else {
+        const double cF = cdot<K>(m.fx, m.fy);
+        const double cu = cdot<K>(m.ux, m.uy);
+        return p.w[K] * (p.inv_cs_2 * (cF - uF) + p.inv_cs_4 * (cu * cF));
+    }
+}
+
+template <int FORCING, int K = 0>
+__device__ __forceinline__ void guo_mrt_all(const KParams &p, const Moments &m,
+                                            double uF, double phi[Q])
+{
+    phi[K] = guo_mrt<K, FORCING>(p, m, uF);
+    if constexpr (K + 1 < Q) guo_mrt_all<FORCING, K + 1>(p, m, uF, phi);
+}
+
+// MRT with the reference's rates S = (1, 1, 1, 1, 1, 1, 1, s7, s8)
+// (base/collision_operator.py:159-163).  With P the projector on the two
+// stress moments (rows 7, 8 of M, squared norm 4):
+//   g = feq + Phi/2 + Minv diag(0..0, 1-s7, 1-s8) M (f - feq + Phi/2)
+// so only two non-equilibrium moments are ever formed:
+//   A = row7 . h,  B = row8 . h,  h = f - feq + Phi/2
+//   g_k = feq_k + Phi_k/2 + (1-s7)/4 * row7_k * A + (1-s8)/4 * row8_k * B
+// Algebraically identical to mrt_all() for these rates (checked against the
+// oracle's full-matrix form to 1e-12).
+// feq and Phi/2 of a direction K and of its opposite inv(K) share their even
+// part (c -> -c flips only the terms that are odd in c):
+//   feq_{K,inv}  = w rho ((1 - u2/(2cs2) + (c.u)^2/(2cs4)) +- (c.u)/cs2)
+//   Phi_{K,inv}  = w ((c.u)(c.F)/cs4 - u.F/cs2 +- (c.F)/cs2)
+// MRT only (our definition); the BGK paths keep the reference's operand order.
+template <int K, int FORCING>
+__device__ __forceinline__ void mrt_pair(const KParams &p, const Moments &m,
+                                         double base, double uF, double e[Q],
+                                         double half_phi[Q])
+{
+    constexpr int KI = d_inv[K];
+    const double cu = cdot<K>(m.ux, m.uy);
+    const double wrho = p.w[K] * m.rho;
+    const double even = base + (0.5 * p.inv_cs_4 * cu) * cu;
+    const double odd = p.inv_cs_2 * cu;
+    e[K] = wrho * (even + odd);
+    e[KI] = wrho * (even - odd);
+    if constexpr (FORCING != 0) {
+        const double cF = cdot<K>(m.fx, m.fy);
+        const double hw = 0.5 * p.w[K];
+        const double r = p.inv_cs_2 * cF;
+        if constexpr (FORCING == 1) {
+            half_phi[K] = hw * r;
+            half_phi[KI] = -(hw * r);
+        } else {
+            const double s = p.inv_cs_4 * (cu * cF) - p.inv_cs_2 * uF;
+            half_phi[K] = hw * (s + r);
+            half_phi[KI] = hw * (s - r);
+        }
+    }
+}
+
+template <int FORCING>
+__device__ __forceinline__ void mrt_reduced_all(const KParams &p,
+                                                const Moments &m, double u2,
+                                                const double f[Q], double g[Q])
+{
+    double e[Q], half_phi[Q];
+    const double base = 1.0 - 0.5 * p.inv_cs_2 * u2;
+    const double uF = m.ux * m.fx + m.uy * m.fy;
+    e[0] = (p.w[0] * m.rho) * base;
+    half_phi[0] = (FORCING == 2) ? -(0.5 * p.w[0] * p.inv_cs_2) * uF : 0.0;
+    mrt_pair<1, FORCING>(p, m, base, uF, e, half_phi);
+    mrt_pair<2, FORCING>(p, m, base, uF, e, half_phi);
+    mrt_pair<5, FORCING>(p, m, base, uF, e, half_phi);
+    mrt_pair<8, FORCING>(p, m, base, uF, e, half_phi);
+    if constexpr (FORCING != 0) {
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+            g[k] = e[k] + half_phi[k];      // feq + Phi/2
+            e[k] = e[k] - half_phi[k];      // so that h = f - e
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < Q; ++k) g[k] = e[k];
+    }
+    const double A = ((f[1] - e[1]) + (f[3] - e[3])) -
+                     ((f[2] - e[2]) + (f[4] - e[4]));
+    const double B = ((f[5] - e[5]) + (f[7] - e[7])) -
+                     ((f[6] - e[6]) + (f[8] - e[8]));
+    const double a = (0.25 * (1.0 - p.s[7])) * A;
+    const double b = (0.25 * (1.0 - p.s[8])) * B;
+    g[1] += a; g[3] += a; g[2] -= a; g[4] -= a;
+    g[5] += b; g[7] += b; g[6] -= b; g[8] -= b;
+}
+
 // Phases 2-5 for one node: moments, then post-collision populations g.
+// COLL: 0 BGK, 1 MRT with nine free rates, 2 MRT with the reference's rates.
 template <int COLL, int FORCING>
 __device__ __forceinline__ Moments collide(const KParams &p, const double f[Q],
                                            double g[Q])
@@ -225,7 +327,8 @@ __device__ __forceinline__ Moments collide(const KParams &p, const double f[Q],
     const Moments m = moments(p, f);
     const double u2 = m.ux * m.ux + m.uy * m.uy;
     if constexpr (COLL == 0) bgk_all<FORCING>(p, m, u2, f, g);
-    else mrt_all<FORCING>(p, m, u2, f, g);
+    else if constexpr (COLL == 1) mrt_all<FORCING>(p, m, u2, f, g);
+    else mrt_reduced_all<FORCING>(p, m, u2, f, g);
     return m;
 }
 

@@ -412,6 +412,7 @@ static void dispatch(int collision, int forcing, bool store, Args &&...args)
     }
     PLB_CASE(0, 0) PLB_CASE(0, 1) PLB_CASE(0, 2)
     PLB_CASE(1, 0) PLB_CASE(1, 1) PLB_CASE(1, 2)
+    PLB_CASE(2, 0) PLB_CASE(2, 1) PLB_CASE(2, 2)
 #undef PLB_CASE
 }
 

@@ -104,6 +104,14 @@ def _mrt(sim):
     return sim
 
 
+def _mrt_free_rates(sim):
+    """Nine free relaxation rates -> the general moment-space kernel."""
+    sim.collision_dict["fluid"]["model"] = "MRT"
+    sim.collision_dict["fluid"]["mrt_rates"] = [1.0, 1.4, 1.3, 1.0, 1.2, 1.0,
+                                                1.2, 1.7, 1.6]
+    return sim
+
+
 def _zero_gradient_outlet(sim):
     sim.boundary_dict["outlet"]["fluid"] = {"type": "zero_gradient"}
     return sim
@@ -116,6 +124,10 @@ ORACLE_ONLY_CASES = {
     "mrt_poiseuille_guo1": lambda: _mrt(cases.poiseuille(forcing="guo_linear")),
     "mrt_cylinder": lambda: _mrt(cases.cylinder()),
     "mrt_periodic_box": lambda: _mrt(cases.periodic_box()),
+    "mrt_free_rates_box": lambda: _mrt_free_rates(cases.periodic_box()),
+    "mrt_free_rates_cavity": lambda: _mrt_free_rates(cases.cavity()),
+    "mrt_free_rates_guo1": lambda: _mrt_free_rates(
+        cases.poiseuille(forcing="guo_linear")),
     "zero_gradient_outlet": lambda: _zero_gradient_outlet(
         cases.inflow_cylinder()),
     "mrt_zero_gradient": lambda: _mrt(_zero_gradient_outlet(
