@@ -348,12 +348,23 @@ class Obstacle:
                 solid_id[block] = np.where(hit, body.id, solid_id[block])
                 own = hit & ~ghost
                 density[block] = np.where(own, body.solid_density, density[block])
+                # The reference never exchanges `velocity`, so a solid node in
+                # the ghost ring has zero wall velocity: true of a periodic
+                # image on one rank (kept, it is what the golden runs contain)
+                # but, on several ranks, it would make the moving-wall term
+                # depend on where the slabs are cut.  Ghost nodes that stand
+                # for a node of the neighbouring slab therefore carry that
+                # node's rigid-body velocity: results do not depend on the
+                # decomposition and equal the single-rank reference.
+                in_domain = ((i_glob >= 0) & (i_glob < int(grid[0])) &
+                             (j_glob >= 0) & (j_glob < int(grid[1])))
+                moving = hit & (~ghost | in_domain)
                 vel = velocity[block]
                 vel[..., 0] = np.where(
-                    own, body.linear_velocity[0] - body.angular_velocity * ry,
+                    moving, body.linear_velocity[0] - body.angular_velocity * ry,
                     vel[..., 0])
                 vel[..., 1] = np.where(
-                    own, body.linear_velocity[1] + body.angular_velocity * rx,
+                    moving, body.linear_velocity[1] + body.angular_velocity * rx,
                     vel[..., 1])
 
     # -- obstacle boundary nodes and normals -----------------------------------

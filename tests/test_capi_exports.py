@@ -1,0 +1,59 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol that
+include/plb.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from pylabolt_b200 import build as plb_build
+from pylabolt_b200 import capi
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(REPO, "include", "plb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(plb_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_library_exports_every_declared_symbol(strict):
+    plb_build.build()
+    path = plb_build.lib_path(strict)
+    assert os.path.exists(path), "run python -m pylabolt_b200.build"
+    lib = ctypes.CDLL(path)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), name
+
+
+def test_python_binding_covers_the_header():
+    assert sorted(capi.EXPORTS) == declared_symbols()
+
+
+def test_config_struct_matches_header_layout():
+    """plb_config is plain C: 2 int32, 2 int64, 6 int32, then doubles."""
+    assert ctypes.sizeof(capi.PlbConfig) == 8 + 16 + 24 + 8 * (1 + 9 + 2 + 2 + 1 + 9)
+    assert capi.PlbConfig.omega.offset == 48
+    assert capi.PlbConfig.weights.offset == 48 + 8 * 15
+
+
+def test_no_cpu_fallback(monkeypatch):
+    """A missing library is an error, not a silent fallback."""
+    monkeypatch.setattr(plb_build, "LIB_DIR", "/nonexistent")
+    monkeypatch.setattr(capi, "_libs", {})
+    with pytest.raises(capi.PlbError, match="no CPU fallback"):
+        capi.load_library(strict=False)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "pylabolt_b200")
+    for root, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, name)).read()
+                assert "import oracle" not in text and "from oracle" not in text
+                assert "liboracle" not in text
