@@ -63,7 +63,7 @@ def load_library(strict=None):
     strict = bool(strict)
     if strict in _libs:
         return _libs[strict]
-    path = _build.lib_path(strict)
+    path = os.environ.get("PLB_LIB") or _build.lib_path(strict)
     if not os.path.exists(path):
         raise PlbError(
             f"{path} is missing: the b200 back end has no CPU fallback. "

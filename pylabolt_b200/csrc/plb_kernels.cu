@@ -25,13 +25,62 @@ namespace plb {
 // ---------------------------------------------------------------------------
 // memory access helpers
 // ---------------------------------------------------------------------------
+// PLB_LD_MODE / PLB_ST_MODE: 0 default, 1 streaming (.cs), 2 (loads only)
+// read-only path without L1 allocation.  The populations are touched exactly
+// once per step, so nothing is gained by keeping them in L1 / L2.
+#ifndef PLB_LD_MODE
+#define PLB_LD_MODE 0
+#endif
+#ifndef PLB_ST_MODE
+#define PLB_ST_MODE 0
+#endif
+#ifndef PLB_BLOCK
+#define PLB_BLOCK 128
+#endif
+
+// Resident CTAs per SM requested from ptxas for the 128-bit bulk kernel.  The
+// kernel is latency bound on HBM: what matters is bytes in flight per SM, i.e.
+// occupancy, so registers are capped as low as each instantiation allows
+// without spilling (measured on B200, profiles/r01_occupancy_sweep.txt:
+// 6 CTAs x 128 threads = 80 registers reaches the measured copy bandwidth;
+// the Guo second-order MRT kernel needs 96 registers, the nine-rate MRT 120).
+__host__ __device__ constexpr int bulk_min_blocks(int coll, int forcing)
+{
+#ifdef PLB_MINBLOCKS
+    return PLB_MINBLOCKS;
+#else
+    return coll == 1 ? 4 : ((coll == 2 && forcing == 2) ? 5 : 6);
+#endif
+}
+
 __device__ __forceinline__ double2 ld2(const double *p)
 {
+#if PLB_LD_MODE == 1
+    return __ldcs(reinterpret_cast<const double2 *>(p));
+#elif PLB_LD_MODE == 2
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
     return *reinterpret_cast<const double2 *>(p);
+#endif
 }
 __device__ __forceinline__ void st2(double *p, double a, double b)
 {
+#if PLB_ST_MODE == 1
+    __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b));
+#else
     *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+#endif
+}
+__device__ __forceinline__ void st1(double *p, double a)
+{
+#if PLB_ST_MODE == 1
+    __stcs(p, a);
+#else
+    *p = a;
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -79,13 +128,13 @@ k_bulk_scalar(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
 // fall back to 8-byte stores.  Any warp that contains a non-bulk node takes
 // the scalar path (domain edges, obstacle surfaces).
 template <int COLL, int FORCING, bool STORE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(PLB_BLOCK, bulk_min_blocks(COLL, FORCING))
 k_bulk_vec2(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
 {
     const Layout &L = a.p.L;
     const int64_t row = blockIdx.x / chunks_per_row;
     const int32_t chunk = blockIdx.x - row * chunks_per_row;
-    const int64_t y = int64_t(chunk) * 256 + 2 * threadIdx.x;
+    const int64_t y = int64_t(chunk) * (2 * PLB_BLOCK) + 2 * threadIdx.x;
     const int64_t idx = L.at(x_begin + row, y);
     const int lane = threadIdx.x & 31;
 
@@ -127,14 +176,14 @@ k_bulk_vec2(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
             // values move to y+1, y+2: pair [y, y+1] = (left lane's b, own a)
             const double up = __shfl_up_sync(0xffffffffu, gb[k], 1);
             if (lane != 0) st2(dst, up, ga[k]);
-            else dst[1] = ga[k];
-            if (lane == 31) dst[2] = gb[k];
+            else st1(dst + 1, ga[k]);
+            if (lane == 31) st1(dst + 2, gb[k]);
         } else {
             // values move to y-1, y: pair [y, y+1] = (own b, right lane's a)
             const double dn = __shfl_down_sync(0xffffffffu, ga[k], 1);
             if (lane != 31) st2(dst, gb[k], dn);
-            else dst[0] = gb[k];
-            if (lane == 0) dst[-1] = ga[k];
+            else st1(dst, gb[k]);
+            if (lane == 0) st1(dst - 1, ga[k]);
         }
     }
 }
@@ -432,8 +481,9 @@ struct BulkVec2 {
     static void run(const StepArgs &a, int64_t x_begin, int64_t n_rows,
                     cudaStream_t st)
     {
-        const int32_t chunks = int32_t((a.p.L.ny + 255) / 256);
-        k_bulk_vec2<C, F, S><<<unsigned(n_rows * chunks), 128, 0, st>>>(
+        constexpr int span = 2 * PLB_BLOCK;
+        const int32_t chunks = int32_t((a.p.L.ny + span - 1) / span);
+        k_bulk_vec2<C, F, S><<<unsigned(n_rows * chunks), PLB_BLOCK, 0, st>>>(
             a, x_begin, chunks);
     }
 };

@@ -196,6 +196,17 @@ def generate(case_name, factory, kwargs, record_steps, comm, out_dir):
                 solver = build_reference_solver(simulation, comm)
             data = snapshot_setup(solver)
             fields = solver.state.fields
+            if case_name == "cylinder":
+                # what the reference writes at t = start_time
+                # (utils/io_operator.py:158-190 + dump_metadata :96-156)
+                solver.state.control.save_interval = 1
+                solver.io_operator.write_fields(solver.state, solver.backend, 0)
+                solver.state.control.save_interval = None
+                saved = np.load(os.path.join("output", "fields", "t_0.npz"))
+                for key in saved.files:
+                    data["io_" + key] = saved[key]
+                data["io_metadata_json"] = np.array(
+                    open("metadata.json").read())
             for step in range(1, max(record_steps) + 1):
                 solver.single_time_step()
                 if step in record_steps:
