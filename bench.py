@@ -130,9 +130,11 @@ def workload_sizes(name, n_ranks, scale):
 # helpers
 # --------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region: the
+    sampler runs from before the warm-up, samples carry nvidia-smi's own
+    timestamp and only those inside [mark_start, mark_stop] are used."""
 
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,"
              "clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,"
@@ -142,6 +144,7 @@ class ClockSampler:
         self.device = device
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -151,21 +154,31 @@ class ClockSampler:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device),
                  "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=self.out, stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=self.out, stderr=subprocess.DEVNULL)
+            deadline = time.time() + 5.0
+            while time.time() < deadline and os.path.getsize(self.path) == 0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return None
-        time.sleep(0.05)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         self.out.close()
-        sm, sm_max, power, reasons = [], [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                  "sw_power_cap"]
         with open(self.path) as f:
@@ -174,20 +187,30 @@ class ClockSampler:
                 if len(parts) < 8:
                     continue
                 try:
-                    sm.append(float(parts[1]))
-                    sm_max.append(float(parts[2]))
-                    power.append(float(parts[3]))
+                    stamp = datetime.datetime.strptime(
+                        parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((stamp, float(parts[1]), float(parts[2]),
+                                 float(parts[3]),
+                                 [n for n, flag in zip(names, parts[4:8])
+                                  if flag.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for name, flag in zip(names, parts[4:8]):
-                    if flag.lower().startswith("active"):
-                        reasons.add(name)
         os.unlink(self.path)
-        if not sm:
+        inside = [r for r in rows
+                  if self.t0 is None or self.t0 - 0.03 <= r[0] <= self.t1 + 0.03]
+        where = "timed region"
+        if not inside and rows:
+            # region shorter than the sampling period: nearest samples
+            mid = 0.5 * (self.t0 + self.t1)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:2]
+            where = "nearest samples (region shorter than sampling period)"
+        if not inside:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(sm_max)),
-                "power_w_max": float(max(power)), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        reasons = sorted({n for r in inside for n in r[4]})
+        return {"sm_mhz": float(np.median([r[1] for r in inside])),
+                "sm_max_mhz": float(max(r[2] for r in inside)),
+                "power_w_max": float(max(r[3] for r in inside)),
+                "samples": len(inside), "window": where, "reasons": reasons}
 
 
 def hbm_peak():
@@ -310,20 +333,22 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device):
     info = plb.info()
 
     # ---- device-resident throughput -------------------------------------
+    sampler = ClockSampler(device)
+    sampler.start()
     plb.initialize_pop()
     plb.step(warmup, False)
     plb.sync()
     comm.Barrier()
-    sampler = ClockSampler(device)
-    sampler.start()
     plb.kernel_launches(reset=True)
     plb.profile_enable(True)
     plb.sync()
     comm.Barrier()
+    sampler.mark_start()
     plb.event_record(0)
     plb.step(steps, False)
     plb.event_record(1)
     plb.sync()
+    sampler.mark_stop()
     comm.Barrier()
     ms = plb.event_elapsed_ms(0, 1)
     launches = plb.kernel_launches()

@@ -135,11 +135,17 @@ int plb_initialize_pop(plb_handle h);
 /* ---- the hot path ------------------------------------------------------ */
 
 /* Advances n_steps reference time steps (Solver.single_time_step,
- * pylabolt/solvers/fluidLB.py:206-253, phases 2-8 fused).  If store_moments
- * is non-zero the LAST step also stores rho and u (phases 2-4 of that step),
- * which is what fields.density / fields.velocity hold after the reference
- * has executed the same number of steps. */
-int plb_step(plb_handle h, int64_t n_steps, int32_t store_moments);
+ * pylabolt/solvers/fluidLB.py:206-253, phases 2-8 fused).  flags apply to the
+ * LAST of the n_steps:
+ *   PLB_STORE_MOMENTS  the step also stores rho and u (phases 2-4 of that
+ *                      step), which is what fields.density / fields.velocity
+ *                      hold after the reference has executed the same steps;
+ *   PLB_RECORD_LINKS   the step also records, per link node and direction,
+ *                      the momentum it exchanged with a wall / solid / edge,
+ *                      for plb_download_link_exchange. */
+#define PLB_STORE_MOMENTS 1
+#define PLB_RECORD_LINKS 2
+int plb_step(plb_handle h, int64_t n_steps, int32_t flags);
 int plb_sync(plb_handle h);
 
 /* ---- diagnostics ("next" rows) ----------------------------------------- */
@@ -148,6 +154,20 @@ int plb_sync(plb_handle h);
  * out = {num_rho, den_rho, num_ux, den_ux, num_uy, den_uy}; the library keeps
  * field_old and updates it, like cpu/compute_residues_kernels.py:6-73. */
 int plb_residue_sums(plb_handle h, double out[6]);
+
+/* Momentum exchange for wall and obstacle forces
+ * (pylabolt/parallel/cpu/force_torque_kernels.py:11-141).  Link nodes are the
+ * fluid nodes on a domain edge or next to a solid node.  plb_link_nodes
+ * returns their padded flat indices in list order (padded_index may be NULL to
+ * query the count).  plb_download_link_exchange returns, for link node i and
+ * direction k = 1..8, out[8*i + k-1] = pop[i,k] + pop_new[i,inv k] of the last
+ * step run with PLB_RECORD_LINKS when the node itself wrote pop_new[i,inv k]
+ * (bounce back, boundary element, uncovered edge), else 0; the force of the
+ * link is c_k times that value.  Links owned by zero_gradient elements are
+ * not recorded. */
+int plb_link_nodes(plb_handle h, int64_t *padded_index, int64_t capacity,
+                   int64_t *n_links);
+int plb_download_link_exchange(plb_handle h, double *out, int64_t n_values);
 
 /* ---- multi-GPU (x-slabs, one process per GPU) -------------------------- */
 

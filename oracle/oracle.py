@@ -196,6 +196,29 @@ class Oracle:
         return (np.sqrt(s[0] / (s[1] + eps)), np.sqrt(s[2] / (s[3] + eps)),
                 np.sqrt(s[4] / (s[5] + eps)))
 
+    def boundary_force(self, n):
+        """Force on boundary element n (cpu/force_torque_kernels.py:100-141)."""
+        out = (ctypes.c_double * 2)()
+        self.lib.oracle_boundary_force(ctypes.byref(self.fields),
+                                       ctypes.byref(self.elements[n]), out)
+        return np.array(out[:])
+
+    def obstacle_force_torque(self, solid_id, fluid_boundary, offset,
+                              grid_global_shape, ref_point, current_solid_id):
+        """(fx, fy, torque) on one obstacle (force_torque_kernels.py:11-94)."""
+        sid = np.ascontiguousarray(solid_id, dtype=np.int64)
+        fb = np.ascontiguousarray(fluid_boundary, dtype=np.uint8)
+        off = (ctypes.c_int64 * 2)(int(offset[0]), int(offset[1]))
+        grid = (ctypes.c_int64 * 2)(int(grid_global_shape[0]),
+                                    int(grid_global_shape[1]))
+        ref = (ctypes.c_double * 2)(float(ref_point[0]), float(ref_point[1]))
+        out = (ctypes.c_double * 3)()
+        self.lib.oracle_obstacle_force_torque(
+            ctypes.byref(self.params), ctypes.byref(self.fields),
+            _ptr(sid, _c_i64_p), _ptr(fb, _c_u8_p), off, grid, ref,
+            ctypes.c_int64(int(current_solid_id)), out)
+        return np.array(out[:])
+
     @property
     def max_threads(self):
         return int(self.lib.oracle_max_threads())

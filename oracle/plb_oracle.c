@@ -477,3 +477,76 @@ void oracle_residue_sums(const oracle_params *p, oracle_fields *f,
     }
     out[0] = nr; out[1] = dr; out[2] = nx; out[3] = dx; out[4] = ny; out[5] = dy;
 }
+
+/* cpu/force_torque_kernels.py:100-141 compute_boundary_force_single_phase:
+ * momentum exchange over the three links of every (non-solid) node of one
+ * boundary element, with pop = post-collision and pop_new = post-stream
+ * populations of the same step.  Reduction order is unspecified upstream. */
+void oracle_boundary_force(const oracle_fields *f, const oracle_element *e,
+                           double out[2])
+{
+    double fx = 0., fy = 0.;
+#pragma omp parallel for schedule(static) reduction(+ : fx, fy)
+    for (int64_t it = 0; it < e->n_nodes; ++it) {
+        int64_t ind = e->nodes[it];
+        if (!f->solid[ind]) {
+            for (int k = 0; k < 3; ++k) {
+                int64_t o = e->out_list[k], v = e->inv_list[k];
+                fx += f->pop[Q * ind + o] * (double)CX[o] -
+                      f->pop_new[Q * ind + v] * (double)CX[v];
+                fy += f->pop[Q * ind + o] * (double)CY[o] -
+                      f->pop_new[Q * ind + v] * (double)CY[v];
+            }
+        }
+    }
+    out[0] = fx; out[1] = fy;
+}
+
+/* cpu/force_torque_kernels.py:11-94 compute_force_torque_single_phase:
+ * force and torque (about ref_point, minimum image) on the obstacle
+ * `current_solid_id`, summed over its fluid boundary nodes and their links
+ * into solid nodes. */
+void oracle_obstacle_force_torque(const oracle_params *p, const oracle_fields *f,
+                                  const int64_t *solid_id,
+                                  const uint8_t *fluid_boundary,
+                                  const int64_t offset[2],
+                                  const int64_t grid_global_shape[2],
+                                  const double ref_point[2],
+                                  int64_t current_solid_id, double out[3])
+{
+    const int64_t size = p->nx_pad * p->ny_pad, nyp = p->ny_pad;
+    const double Nx = (double)grid_global_shape[0], Ny = (double)grid_global_shape[1];
+    double fx = 0., fy = 0., tq = 0.;
+#pragma omp parallel for schedule(static) reduction(+ : fx, fy, tq)
+    for (int64_t ind = 0; ind < size; ++ind) {
+        if (!f->ghost[ind] && fluid_boundary[ind] &&
+            solid_id[ind] == current_solid_id) {
+            int64_t x = ind / nyp, y = ind - x * nyp;
+            double rx = (double)(x - 1 + offset[0]) - ref_point[0];
+            double ry = (double)(y - 1 + offset[1]) - ref_point[1];
+            double rx_min = rx, ry_min = ry;
+            if (p->x_periodic) {
+                if (__builtin_fabs(rx + Nx) < __builtin_fabs(rx_min)) rx_min = rx + Nx;
+                if (__builtin_fabs(rx - Nx) < __builtin_fabs(rx_min)) rx_min = rx - Nx;
+            }
+            if (p->y_periodic) {
+                if (__builtin_fabs(ry + Ny) < __builtin_fabs(ry_min)) ry_min = ry + Ny;
+                if (__builtin_fabs(ry - Ny) < __builtin_fabs(ry_min)) ry_min = ry - Ny;
+            }
+            for (int k = 0; k < Q; ++k) {
+                int64_t nb = (x + CX[k]) * nyp + (y + CY[k]);
+                if (f->solid[nb]) {
+                    int64_t ki = INV[k];
+                    double vx = f->pop[Q * ind + k] * (double)CX[k] -
+                                f->pop_new[Q * ind + ki] * (double)CX[ki];
+                    double vy = f->pop[Q * ind + k] * (double)CY[k] -
+                                f->pop_new[Q * ind + ki] * (double)CY[ki];
+                    fx += vx;
+                    fy += vy;
+                    tq += rx_min * vy - ry_min * vx;
+                }
+            }
+        }
+    }
+    out[0] = fx; out[1] = fy; out[2] = tq;
+}

@@ -30,7 +30,9 @@ EXPORTS = [
     "plb_event_record", "plb_event_elapsed_ms", "plb_kernel_launches",
     "plb_host_alloc", "plb_host_free", "plb_flush_l2",
     "plb_profile_enable", "plb_profile_read", "plb_info",
+    "plb_link_nodes", "plb_download_link_exchange",
 ]
+STORE_MOMENTS, RECORD_LINKS = 1, 2
 
 
 class PlbConfig(ctypes.Structure):
@@ -99,6 +101,9 @@ def load_library(strict=None):
     lib.plb_profile_read.argtypes = [vp, ctypes.POINTER(dbl),
                                      ctypes.POINTER(i64)]
     lib.plb_info.argtypes = [vp, ctypes.POINTER(i64)]
+    lib.plb_link_nodes.argtypes = [vp, ctypes.POINTER(i64), i64,
+                                   ctypes.POINTER(i64)]
+    lib.plb_download_link_exchange.argtypes = [vp, ctypes.POINTER(dbl), i64]
     _libs[strict] = lib
     return lib
 
@@ -241,9 +246,30 @@ class Plb:
         self._check(self.lib.plb_initialize_pop(self._h))
 
     # -- the hot path --------------------------------------------------------
-    def step(self, n_steps=1, store_moments=False):
-        self._check(self.lib.plb_step(self._h, int(n_steps),
-                                      int(bool(store_moments))))
+    def step(self, n_steps=1, store_moments=False, record_links=False):
+        flags = (STORE_MOMENTS if store_moments else 0) | \
+            (RECORD_LINKS if record_links else 0)
+        self._check(self.lib.plb_step(self._h, int(n_steps), flags))
+
+    def link_nodes(self):
+        """Padded flat indices of the link nodes, in list order."""
+        n = ctypes.c_int64()
+        self._check(self.lib.plb_link_nodes(self._h, None, 0, ctypes.byref(n)))
+        out = np.empty(n.value, dtype=np.int64)
+        if n.value:
+            self._check(self.lib.plb_link_nodes(
+                self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                n.value, ctypes.byref(n)))
+        return out
+
+    def link_exchange(self, n_links):
+        """(n_links, 8): pop[k] + pop_new[inv k] per link node and k = 1..8."""
+        out = np.zeros((n_links, 8), dtype=np.float64)
+        if n_links:
+            self._check(self.lib.plb_download_link_exchange(
+                self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                out.size))
+        return out
 
     def sync(self):
         self._check(self.lib.plb_sync(self._h))

@@ -126,6 +126,8 @@ struct plb_solver {
     double *staging = nullptr;
     size_t staging_bytes = 0;
     double *flush_buf = nullptr;
+    double *exch_dev = nullptr;          // n_links x 8 momentum exchange (lazy)
+    std::vector<int64_t> link_inds;      // padded flat index of each link node
 
     std::vector<uint8_t> solid_host;
     std::vector<ElementHost> elements;
@@ -321,7 +323,7 @@ int bulk_timed(plb_solver *s, const StepArgs &a, int64_t x0, int64_t x1)
     return PLB_OK;
 }
 
-int step_once(plb_solver *s, bool store)
+int step_once(plb_solver *s, bool store, bool record)
 {
     const Layout &L = s->L;
     StepArgs a;
@@ -335,6 +337,12 @@ int step_once(plb_solver *s, bool store)
     a.collision = s->kernel_collision;
     a.forcing = s->cfg.forcing;
     a.store = store ? 1 : 0;
+    a.exch = nullptr;
+    if (record && s->n_links > 0) {
+        if (!s->exch_dev)
+            CUDA_TRY(cudaMalloc(&s->exch_dev, size_t(s->n_links) * 8 * sizeof(double)));
+        a.exch = s->exch_dev;
+    }
     double *fout = a.fout;
     const int32_t right_dirs[3] = {1, 5, 8}, left_dirs[3] = {3, 6, 7};
     const bool faces = s->cfg.left_neighbor || s->cfg.right_neighbor;
@@ -516,6 +524,7 @@ void plb_destroy(plb_handle s)
     cudaFree(s->code);
     cudaFree(s->staging);
     cudaFree(s->flush_buf);
+    cudaFree(s->exch_dev);
     cudaFree(s->elements_dev);
     cudaFree(s->links_dev);
     for (auto &z : s->zg_dev) cudaFree(z.first);
@@ -661,6 +670,9 @@ int plb_finalize_geometry(plb_handle s)
     // device copies
     CUDA_TRY(cudaMemcpy(s->code, code.data(), code.size(), cudaMemcpyHostToDevice));
     s->n_links = int64_t(link_nodes.size());
+    s->link_inds.resize(link_nodes.size());
+    for (size_t i = 0; i < link_nodes.size(); ++i)
+        s->link_inds[i] = (int64_t(link_nodes[i].x) + 1) * nyp + link_nodes[i].y + 1;
     if (s->n_links) {
         CUDA_TRY(cudaMalloc(&s->links_dev, link_nodes.size() * sizeof(LinkNode)));
         CUDA_TRY(cudaMemcpy(s->links_dev, link_nodes.data(),
@@ -776,15 +788,48 @@ int plb_initialize_pop(plb_handle s)
     return PLB_OK;
 }
 
-int plb_step(plb_handle s, int64_t n_steps, int32_t store_moments)
+int plb_step(plb_handle s, int64_t n_steps, int32_t flags)
 {
     if (!s) return fail(PLB_ERR_INVALID, "null handle");
     if (!s->finalized) return fail(PLB_ERR_STATE, "plb_finalize_geometry not called");
     if (n_steps < 0) return fail(PLB_ERR_INVALID, "n_steps < 0");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
-    for (int64_t i = 0; i < n_steps; ++i)
-        if (int rc = step_once(s, store_moments && i == n_steps - 1)) return rc;
+    for (int64_t i = 0; i < n_steps; ++i) {
+        const bool last = i == n_steps - 1;
+        if (int rc = step_once(s, last && (flags & PLB_STORE_MOMENTS),
+                               last && (flags & PLB_RECORD_LINKS)))
+            return rc;
+    }
     CUDA_TRY(cudaGetLastError());
+    return PLB_OK;
+}
+
+int plb_link_nodes(plb_handle s, int64_t *padded_index, int64_t capacity,
+                   int64_t *n_links)
+{
+    if (!s || !n_links) return fail(PLB_ERR_INVALID, "null argument");
+    if (!s->finalized) return fail(PLB_ERR_STATE, "plb_finalize_geometry not called");
+    *n_links = s->n_links;
+    if (padded_index) {
+        if (capacity < s->n_links)
+            return fail(PLB_ERR_INVALID, "capacity %lld < %lld link nodes",
+                        (long long)capacity, (long long)s->n_links);
+        memcpy(padded_index, s->link_inds.data(), size_t(s->n_links) * sizeof(int64_t));
+    }
+    return PLB_OK;
+}
+
+int plb_download_link_exchange(plb_handle s, double *out, int64_t n_values)
+{
+    if (!s || !out) return fail(PLB_ERR_INVALID, "null argument");
+    if (n_values != s->n_links * 8)
+        return fail(PLB_ERR_INVALID, "expected %lld values", (long long)(s->n_links * 8));
+    if (!s->exch_dev)
+        return fail(PLB_ERR_STATE, "no step was run with PLB_RECORD_LINKS");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(out, s->exch_dev, size_t(n_values) * sizeof(double),
+                             cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     return PLB_OK;
 }
 

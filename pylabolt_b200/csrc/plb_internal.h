@@ -85,6 +85,7 @@ struct StepArgs {
     double *fout;
     const uint8_t *code;
     double *rho, *ux, *uy;   // moment planes (ux/uy also hold solid velocities)
+    double *exch;            // per link node x 8: momentum exchange, or null
     int32_t collision, forcing, store;
 };
 

@@ -239,32 +239,36 @@ k_links(StepArgs a, const LinkNode *__restrict__ nodes, int64_t n_nodes,
     for (int q = 1; q < Q; ++q) {
         const int code = int((nd.links >> (8 * (q - 1))) & 0xff);
         const int cx = d_cx[q], cy = d_cy[q], qi = d_inv[q];
+        bool own = true;      // this node writes its own slot f'[i, inv q]
+        double back = 0.0;    // ... with this value
         if (code == LINK_PUSH) {
             a.fout[q * plane + idx + cx * pitch + cy] = g[q];
+            own = false;
         } else if (code == LINK_WRAP) {
             int64_t ty = nd.y + cy;
             if (ty < 0) ty = L.ny - 1;
             else if (ty >= L.ny) ty = 0;
             a.fout[q * plane + L.at(nd.x + cx, ty)] = g[q];
+            own = false;
         } else if (code == LINK_SOLID_BB) {
             // cpu/streaming_kernels.py:40-47 (k_inv = q, ind_nb = target)
             const int64_t t = idx + cx * pitch + cy;
             const double temp = 2 * a.p.w[q] * m.rho * a.p.inv_cs_2 *
                                 (double(cx) * a.ux[t] + double(cy) * a.uy[t]);
-            a.fout[qi * plane + idx] = g[q] - temp;
+            back = g[q] - temp;
         } else if (code == LINK_ZERO) {
             // pulled from a ghost node that nothing ever fills
-            a.fout[qi * plane + idx] = 0.0;
+            back = 0.0;
         } else if (code >= LINK_ELEMENT0) {
             const ElementDev e = elements[code - LINK_ELEMENT0];
             if (e.type == 0) {
                 // bounce_back, cpu/fluid_boundary_kernels.py:21-25
-                a.fout[qi * plane + idx] = g[q];
+                back = g[q];
             } else if (e.type == 1) {
                 // fixed_velocity_density_based, :51-62
                 const double temp = 2 * a.p.w[q] * m.rho * a.p.inv_cs_2 *
                                     (double(cx) * e.v0 + double(cy) * e.v1);
-                a.fout[qi * plane + idx] = g[q] - temp;
+                back = g[q] - temp;
             } else {
                 // fixed_pressure_density_based, :126-152
                 double unx, uny;
@@ -277,10 +281,16 @@ k_links(StepArgs a, const LinkNode *__restrict__ nodes, int64_t n_nodes,
                 const double temp = 2 * a.p.w[q] * e.scalar *
                                     (1 + 0.5 * a.p.inv_cs_4 * cu * cu -
                                      0.5 * a.p.inv_cs_2 * u2);
-                a.fout[qi * plane + idx] = -g[q] + temp;
+                back = -g[q] + temp;
             }
+        } else {
+            own = false;      // LINK_ZG: written by k_zero_gradient afterwards
         }
-        // LINK_ZG: written by k_zero_gradient afterwards
+        if (own) a.fout[qi * plane + idx] = back;
+        // momentum exchanged across the link, for the wall / obstacle force:
+        // pop[k] c_k - pop_new[k_inv] c_kinv = c_k (g_k + f'_kinv)
+        // (cpu/force_torque_kernels.py:73-81, 128-137)
+        if (a.exch) a.exch[i * 8 + (q - 1)] = own ? g[q] + back : 0.0;
     }
 }
 

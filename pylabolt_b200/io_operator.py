@@ -97,6 +97,105 @@ class InputOutputOperator:
     def set_backend(self, state, backend, plb):
         self.plb = plb
 
+    # -- histories: utils/io_operator.py:236-357 ------------------------------
+    def _history_path(self, name):
+        return os.path.join(self.root_dir, "output", "histories", name + ".dat")
+
+    def setup_write_histories(self, state):
+        """Headers of output/histories/<name>.dat, one file per obstacle and
+        per wall boundary element, written by rank 0."""
+        self._histories_ready = True
+        wanted = (state.obstacle.write_obstacle_data or
+                  state.boundary.write_boundary_data)
+        if not wanted or state.domain.mpi_rank != 0:
+            return
+        os.makedirs(os.path.join(self.root_dir, "output", "histories"),
+                    exist_ok=True)
+        if state.obstacle.write_obstacle_data:
+            for body in state.obstacle.obstacles:
+                with open(self._history_path(body.name), "w") as out:
+                    out.write(f"{'#':5} {'PyLaBolt obstacle history'}\n"
+                              f"{'#':5} {'ID':8}: {body.id}\n"
+                              f"{'#':5} {'Name':8}: {body.name}\n"
+                              f"{'#':5} {'Type':8}: {body.type}\n"
+                              f"{'#':5} {'Columns':8}:\n")
+                    out.write(f"{'#':5}{'time':<21}" + "".join(
+                        f"{col:<30}" for col in
+                        ("pos_x", "pos_y", "alpha", "vel_x", "vel_y", "omega",
+                         "force_x", "force_y", "torque")) + "\n")
+        if state.boundary.write_boundary_data:
+            for element in state.boundary.boundary_elements:
+                if not element.wall:
+                    continue
+                with open(self._history_path(element.name), "w") as out:
+                    out.write(f"{'#':5} {'PyLaBolt boundary history'}\n"
+                              f"{'#':5} {'Name':8}: {element.name}\n"
+                              f"{'#':5} {'Columns':8}:\n")
+                    out.write(f"{'#':5}{'time':<21}{'force_x':<30}"
+                              f"{'force_y':<30}\n")
+
+    def write_histories(self, state, time_step):
+        if not getattr(self, "_histories_ready", False):
+            self.setup_write_histories(state)
+        if state.domain.mpi_rank != 0:
+            return
+        ob = state.obstacle
+        if (ob.write_obstacle_data and ob.write_interval is not None and
+                time_step % ob.write_interval == 0):
+            for body in ob.obstacles:
+                values = (body.center[0], body.center[1],
+                          body.inclination_angle, body.linear_velocity[0],
+                          body.linear_velocity[1], body.angular_velocity,
+                          body.force[0], body.force[1], body.torque)
+                with open(self._history_path(body.name), "a") as out:
+                    out.write(f"{time_step:<24}" + "".join(
+                        f"{float(v):<30.16e}" for v in values) + "\n")
+        bd = state.boundary
+        if (bd.write_boundary_data and bd.write_interval is not None and
+                time_step % bd.write_interval == 0):
+            for element in bd.boundary_elements:
+                if not element.wall:
+                    continue
+                with open(self._history_path(element.name), "a") as out:
+                    out.write(f"{time_step:<24}{element.force[0]:<30.16e}"
+                              f"{element.force[1]:<30.16e}\n")
+
+    # -- checkpoints: parsed but never implemented upstream (control.py:35) ----
+    def _checkpoint_path(self, state, time_step):
+        if state.domain.mpi_size == 1:
+            base = os.path.join(self.root_dir, "output", "checkpoints")
+        else:
+            base = os.path.join(self.root_dir, "procs",
+                                "proc_" + str(state.domain.mpi_rank))
+        return os.path.join(base, "checkpoint_t_" + str(time_step) + ".npz")
+
+    def write_checkpoint(self, state, time_step):
+        """Every checkpoint_interval steps: this rank's pop_fluid_new in the
+        reference layout (all a restart needs: rho and u are its moments)."""
+        interval = state.control.checkpoint_interval
+        if interval is None or time_step % interval != 0:
+            return
+        path = self._checkpoint_path(state, time_step)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        np.savez(path, pop_fluid_new=self.plb.download(capi.POP),
+                 time_step=np.int64(time_step),
+                 shape=np.asarray(state.domain.shape, dtype=np.int64))
+
+    def load_checkpoint(self, state, time_step):
+        """start_time > 0 resumes from the checkpoint of that step, if one
+        exists.  Returns True when populations were restored."""
+        if not time_step:
+            return False
+        path = self._checkpoint_path(state, time_step)
+        if not os.path.exists(path):
+            return False
+        data = np.load(path)
+        if not np.array_equal(data["shape"], state.domain.shape):
+            raise ValueError("checkpoint " + path + " was written for a "
+                             "different decomposition")
+        self.plb.upload(capi.POP, data["pop_fluid_new"])
+        return True
+
     def gather_fields(self, state):
         """The arrays of one output file, ghost ring stripped."""
         out = {}

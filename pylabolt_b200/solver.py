@@ -17,6 +17,7 @@ import time
 import numpy as np
 
 from . import capi
+from .force_torque import MomentumExchange
 from .helpers import SimulationStatusLogger, load_simulation, print_log
 from .io_operator import InputOutputOperator
 from .operators import CollisionOperator, FluidLB, ForceOperator
@@ -139,21 +140,65 @@ class Solver:
                           -1 if right is None else right)
         self.residue_operator.set_backend(st, self.backend, plb)
         self.io_operator.set_backend(st, self.backend, plb)
+        self.momentum = None
+        if st.boundary.compute_force or st.obstacle.compute_force_torque:
+            self.momentum = MomentumExchange(st, plb.link_nodes())
         print_log("\nSetting simulation backend done!", rank, verbose)
         print_log("-" * 80, rank, verbose)
 
     # -- reference: Solver.single_time_step, fluidLB.py:206-253 ----------------
-    def single_time_step(self, store_moments=False):
+    def single_time_step(self, store_moments=False, record_links=False):
         """One reference time step: phases 2-8 (moments, gravity force,
         collision, halo exchange, streaming with in-flight bounce back,
         boundary elements) as one fused pass inside libplb.  With
         ``store_moments`` the step also leaves rho / u (phases 2-4) in HBM for
-        output and residues, which the reference does on every step."""
-        self.plb.step(1, store_moments)
+        output and residues, which the reference does on every step; with
+        ``record_links`` it records the momentum exchanged on wall / solid
+        links (phase 9 and BoundaryOperator.compute_force)."""
+        self.plb.step(1, store_moments, record_links)
 
-    def advance(self, n_steps, store_moments_last=False):
+    def advance(self, n_steps, store_moments_last=False, record_links_last=False):
         """``n_steps`` calls of single_time_step in one library call."""
-        self.plb.step(n_steps, store_moments_last)
+        self.plb.step(n_steps, store_moments_last, record_links_last)
+
+    # -- reference: BoundaryOperator.compute_force (boundary_operator.py:204-237)
+    #    and ObstacleOperator.compute_force_torque (obstacle_operator.py:75-109)
+    def compute_forces(self, exchange=None):
+        """Reduces the recorded link exchange to the force on every wall
+        boundary element and the force / torque on every obstacle (summed
+        over ranks) and stores them on the element / obstacle objects."""
+        st = self.state
+        if self.momentum is None:
+            return None, None
+        if exchange is None:
+            exchange = self.plb.link_exchange(self.momentum.n_links)
+        wall_local = self.momentum.boundary_forces(exchange)
+        body_local = self.momentum.obstacle_forces(exchange)
+        wall = np.zeros_like(wall_local)
+        body = np.zeros_like(body_local)
+        self.comm.Allreduce(wall_local, wall)
+        self.comm.Allreduce(body_local, body)
+        for n, element in enumerate(st.boundary.boundary_elements):
+            if element.wall:
+                element.force[:] = wall[n]
+        st.boundary.local_force[:] = wall_local
+        st.boundary.global_force[:] = wall
+        for n, body_obj in enumerate(st.obstacle.obstacles):
+            body_obj.force[:] = body[n, :2]
+            body_obj.torque = body[n, 2]
+        return wall, body
+
+    def _needs_links(self, time_step):
+        st = self.state
+        if self.momentum is None:
+            return False
+        wall = (st.boundary.compute_force and
+                st.boundary.write_interval is not None and
+                time_step % st.boundary.write_interval == 0)
+        body = (st.obstacle.compute_force_torque and
+                st.obstacle.write_interval is not None and
+                time_step % st.obstacle.write_interval == 0)
+        return wall or body
 
     # -- reference: Solver.compile, fluidLB.py:255-284 -------------------------
     def compile(self, verbose=None):
@@ -180,16 +225,24 @@ class Solver:
         rank = st.domain.mpi_rank
         print_log("\n" + "-" * 80, rank, verbose)
         print_log("Running simulation...\n", rank, verbose)
-        self.plb.initialize_pop()
+        if not self.io_operator.load_checkpoint(st, st.control.start_time):
+            self.plb.initialize_pop()
+        if self.momentum is not None:
+            self.compute_forces(self.momentum.initial_exchange(st.lattice))
         self.io_operator.write_fields(st, self.backend, st.control.start_time)
+        self.io_operator.write_histories(st, time_step=0)
         run_time_start = time.perf_counter()
         for time_step in range(st.control.start_time + 1,
                                st.control.end_time + 1):
-            if self._needs_moments(time_step):
-                self.single_time_step(store_moments=True)
+            moments = self._needs_moments(time_step)
+            links = self._needs_links(time_step)
+            if moments or links:
+                self.single_time_step(store_moments=moments, record_links=links)
             else:
                 self.execute_single_time_step()
             self.time_step = time_step
+            if links:
+                self.compute_forces()
             self.residue_operator.compute_residues(st, self.backend, self.comm,
                                                    time_step)
             self.logger.log_data(
@@ -197,6 +250,8 @@ class Solver:
                 res_density=self.residue_operator.residues["res_density"],
                 res_velocity=self.residue_operator.residues["res_velocity"])
             self.io_operator.write_fields(st, self.backend, time_step)
+            self.io_operator.write_histories(st, time_step)
+            self.io_operator.write_checkpoint(st, time_step)
         self.plb.sync()
         run_time = time.perf_counter() - run_time_start
         print_log("\n" + "-" * 80, rank, verbose)

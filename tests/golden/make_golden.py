@@ -186,6 +186,30 @@ def snapshot_setup(solver):
     return out
 
 
+def reference_forces(solver):
+    """Wall and obstacle forces computed by the reference's own kernels
+    (cpu/force_torque_kernels.py) on the current pop / pop_new."""
+    from pylabolt.parallel.cpu.force_torque_kernels import (
+        compute_boundary_force_single_phase,
+        compute_force_torque_single_phase)
+    st = solver.state
+    f, lat = st.fields, st.lattice
+    wall = np.array([
+        compute_boundary_force_single_phase(
+            lat.cx, lat.cy, f.solid, f.pop_fluid, f.pop_fluid_new,
+            el.boundary_nodes, el.out_list, el.inv_list)
+        for el in st.boundary.boundary_elements]).reshape(-1, 2)
+    body = np.array([
+        compute_force_torque_single_phase(
+            st.domain.size, st.domain.shape, st.domain.offset,
+            st.mesh.grid_global_shape, lat.cx, lat.cy, lat.inv_list,
+            lat.no_of_directions, st.boundary.x_periodic,
+            st.boundary.y_periodic, f.solid, f.solid_id, f.fluid_boundary,
+            f.ghost_node, f.pop_fluid, f.pop_fluid_new, ob.ref_point, ob.id)
+        for ob in st.obstacle.obstacles]).reshape(-1, 3)
+    return wall, body
+
+
 def generate(case_name, factory, kwargs, record_steps, comm, out_dir):
     simulation = factory(**kwargs)
     cwd = os.getcwd()
@@ -207,9 +231,13 @@ def generate(case_name, factory, kwargs, record_steps, comm, out_dir):
                     data["io_" + key] = saved[key]
                 data["io_metadata_json"] = np.array(
                     open("metadata.json").read())
+            data["wall_force_0"], data["body_force_0"] = \
+                reference_forces(solver)
             for step in range(1, max(record_steps) + 1):
                 solver.single_time_step()
                 if step in record_steps:
+                    data[f"wall_force_{step}"], data[f"body_force_{step}"] = \
+                        reference_forces(solver)
                     data[f"density_{step}"] = fields.density.copy()
                     data[f"velocity_{step}"] = fields.velocity.copy()
                     data[f"pop_{step}"] = fields.pop_fluid_new.copy()
