@@ -302,7 +302,8 @@ int run_zero_gradient(plb_solver *s, double *fout, cudaStream_t st)
     return PLB_OK;
 }
 
-int bulk_timed(plb_solver *s, const StepArgs &a, int64_t x0, int64_t x1)
+int bulk_timed(plb_solver *s, const StepArgs &a, int64_t x0, int64_t x1,
+               cudaStream_t stream)
 {
     if (x1 <= x0) return PLB_OK;
     if (s->profile) {
@@ -313,11 +314,11 @@ int bulk_timed(plb_solver *s, const StepArgs &a, int64_t x0, int64_t x1)
                 s->prof_events.push_back(e);
             }
         }
-        CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used], s->stream));
+        CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used], stream));
     }
-    s->launches += launch_bulk(a, x0, x1, s->variant, s->stream);
+    s->launches += launch_bulk(a, x0, x1, s->variant, stream);
     if (s->profile) {
-        CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used + 1], s->stream));
+        CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used + 1], stream));
         s->prof_used += 2;
     }
     return PLB_OK;
@@ -348,7 +349,7 @@ int step_once(plb_solver *s, bool store, bool record)
     const bool faces = s->cfg.left_neighbor || s->cfg.right_neighbor;
 
     if (!s->comm) {
-        if (int rc = bulk_timed(s, a, 0, L.nx)) return rc;
+        if (int rc = bulk_timed(s, a, 0, L.nx, s->stream)) return rc;
         s->launches += launch_links(a, s->links_dev, s->n_links, s->elements_dev,
                                     s->stream);
         if (faces) {
@@ -366,14 +367,19 @@ int step_once(plb_solver *s, bool store, bool record)
         }
         run_zero_gradient(s, fout, s->stream);
     } else {
-        // slab edges first, so that the face exchange overlaps the interior
-        if (int rc = bulk_timed(s, a, 0, 1)) return rc;
-        if (L.nx > 1)
-            if (int rc = bulk_timed(s, a, L.nx - 1, L.nx)) return rc;
-        s->launches += launch_links(a, s->links_dev, s->n_links, s->elements_dev,
-                                    s->stream);
+        // Two concurrent chains.  High-priority comm stream: the two slab-edge
+        // columns and the link nodes (everything that feeds a face), the face
+        // exchange and its delivery.  Main stream: the interior columns.  The
+        // chains write disjoint slots of lattice B; they join before the
+        // zero_gradient pass, so the O(perimeter) kernels and the exchange
+        // latency are hidden behind the interior pass.
+        cudaStream_t cs = s->comm_stream;
         CUDA_TRY(cudaEventRecord(s->ev_edge, s->stream));
-        CUDA_TRY(cudaStreamWaitEvent(s->comm_stream, s->ev_edge, 0));
+        CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_edge, 0));
+        if (int rc = bulk_timed(s, a, 0, 1, cs)) return rc;
+        if (L.nx > 1)
+            if (int rc = bulk_timed(s, a, L.nx - 1, L.nx, cs)) return rc;
+        s->launches += launch_links(a, s->links_dev, s->n_links, s->elements_dev, cs);
         NCCL_TRY(g_nccl.GroupStart());
         if (s->right_rank >= 0)
             for (int j = 0; j < 3; ++j)
@@ -405,7 +411,7 @@ int step_once(plb_solver *s, bool store, bool record)
                                               s->recv_right, 0, L.ny, 2 * L.ny,
                                               s->mask_right, s->comm_stream);
         CUDA_TRY(cudaEventRecord(s->ev_comm, s->comm_stream));
-        if (int rc = bulk_timed(s, a, 1, L.nx - 1)) return rc;
+        if (int rc = bulk_timed(s, a, 1, L.nx - 1, s->stream)) return rc;
         CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
         run_zero_gradient(s, fout, s->stream);
     }
@@ -465,6 +471,22 @@ int plb_create(const plb_config *c, plb_handle *out)
     for (int k = 0; k < Q; ++k) {
         p.w[k] = c->weights[k];
         p.s[k] = c->mrt_rates[k];
+    }
+    {
+        MrtStress &t = p.mrt;
+        t.hgx = 0.5 * p.gx;
+        t.hgy = 0.5 * p.gy;
+        t.k2 = 0.5 * p.inv_cs_2;
+        t.k4 = 0.5 * p.inv_cs_4;
+        t.k7 = p.w[1] * p.inv_cs_4;
+        t.k8 = 4.0 * p.w[5] * p.inv_cs_4;
+        t.qa = 0.25 * (1.0 - p.s[7]);
+        t.qb = 0.25 * (1.0 - p.s[8]);
+        const double cg[4] = {p.gx, p.gy, p.gx + p.gy, p.gx - p.gy};
+        for (int j = 0; j < 4; ++j) {
+            t.k4cg[j] = t.k4 * cg[j];
+            t.k2cg[j] = t.k2 * cg[j];
+        }
     }
     if (const char *v = getenv("PLB_KERNEL"))
         s->variant = (strcmp(v, "scalar") == 0) ? 0 : 1;

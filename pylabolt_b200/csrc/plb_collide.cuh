@@ -217,105 +217,90 @@ __device__ __forceinline__ void mrt_all(const KParams &p, const Moments &m,
     for (int k = 0; k < Q; ++k) g[k] = f[k] + dv[k];
 }
 
-// Guo source for the MRT paths.  MRT has no upstream arithmetic to preserve,
-// so the second-order bracket is evaluated in the cheaper, algebraically
-// identical form  w_k * (inv_cs_2 * (c_k.F - u.F) + inv_cs_4 * (c_k.u)(c_k.F)).
-template <int K, int FORCING>
-__device__ __forceinline__ double guo_mrt(const KParams &p, const Moments &m,
-                                          double uF)
-{
-    if constexpr (FORCING == 1) {
-        return guo<K, 1>(p, m);
-    } else if constexpr (K == 0) {
-        return -(p.w[0] * p.inv_cs_2) * uF;
-    } else {
-        const double cF = cdot<K>(m.fx, m.fy);
-        const double cu = cdot<K>(m.ux, m.uy);
-        return p.w[K] * (p.inv_cs_2 * (cF - uF) + p.inv_cs_4 * (cu * cF));
-    }
-}
-
-template <int FORCING, int K = 0>
-__device__ __forceinline__ void guo_mrt_all(const KParams &p, const Moments &m,
-                                            double uF, double phi[Q])
-{
-    phi[K] = guo_mrt<K, FORCING>(p, m, uF);
-    if constexpr (K + 1 < Q) guo_mrt_all<FORCING, K + 1>(p, m, uF, phi);
-}
-
 // MRT with the reference's rates S = (1, 1, 1, 1, 1, 1, 1, s7, s8)
-// (base/collision_operator.py:159-163).  With P the projector on the two
-// stress moments (rows 7, 8 of M, squared norm 4):
-//   g = feq + Phi/2 + Minv diag(0..0, 1-s7, 1-s8) M (f - feq + Phi/2)
-// so only two non-equilibrium moments are ever formed:
-//   A = row7 . h,  B = row8 . h,  h = f - feq + Phi/2
-//   g_k = feq_k + Phi_k/2 + (1-s7)/4 * row7_k * A + (1-s8)/4 * row8_k * B
-// Algebraically identical to mrt_all() for these rates (checked against the
-// oracle's full-matrix form to 1e-12).
-// feq and Phi/2 of a direction K and of its opposite inv(K) share their even
-// part (c -> -c flips only the terms that are odd in c):
-//   feq_{K,inv}  = w rho ((1 - u2/(2cs2) + (c.u)^2/(2cs4)) +- (c.u)/cs2)
-//   Phi_{K,inv}  = w ((c.u)(c.F)/cs4 - u.F/cs2 +- (c.F)/cs2)
-// MRT only (our definition); the BGK paths keep the reference's operand order.
+// (base/collision_operator.py:159-163) -- OUR DEFINITION like mrt_all(), and
+// algebraically identical to it for these rates (checked against the oracle's
+// full-matrix form to 1e-12).  With P_r the projector on stress moment r
+// (rows 7, 8 of M, squared norm 4):
+//   g = feq + Phi/2 + sum_r (1 - s_r) P_r h,      h = f - feq + Phi/2
+// so only the two stress moments of h are ever formed,
+//   A = row7 . h,  B = row8 . h,   g_k = (feq + Phi/2)_k + qa row7_k A + qb row8_k B
+// and the stress moments of feq and Phi are known in closed form (isotropy of
+// the D2Q9 weights; F = rho g is the reference's only force,
+// cpu/force_field_kernels.py:23-25):
+//   row7 . feq = k7 rho (ux^2 - uy^2)        row7 . Phi/2 = k7 rho (ux gx - uy gy)
+//   row8 . feq = k8 rho ux uy                row8 . Phi/2 = k8 rho (ux gy + uy gx)/2
+// (second-order Guo; the linear Guo source has no stress moment), with
+// k7 = w_1/cs^4 and k8 = 4 w_5/cs^4 (both 1 up to the rounding of the
+// reference's cs).  feq + Phi/2 of a direction K and of its opposite share
+// their even part (c -> -c flips only the terms that are odd in c):
+//   (feq + Phi/2)_{K, inv K} = w rho (E +- O)
+//   E = 1 - (u.u + u.g)/(2 cs^2) + (c.u)(c.u + c.g)/(2 cs^4)
+//   O = (c.u + c.g/2)/cs^2
+// 84 fp64 operations per node with second-order Guo forcing (the generic
+// nine-rate transform needs 304), no per-direction temporaries kept live.
 template <int K, int FORCING>
-__device__ __forceinline__ void mrt_pair(const KParams &p, const Moments &m,
-                                         double base, double uF, double e[Q],
-                                         double half_phi[Q])
+__device__ __forceinline__ void stress_pair(const KParams &p, double ux,
+                                            double uy, double wrho, double base,
+                                            double proj, double g[Q])
 {
     constexpr int KI = d_inv[K];
-    const double cu = cdot<K>(m.ux, m.uy);
-    const double wrho = p.w[K] * m.rho;
-    const double even = base + (0.5 * p.inv_cs_4 * cu) * cu;
-    const double odd = p.inv_cs_2 * cu;
-    e[K] = wrho * (even + odd);
-    e[KI] = wrho * (even - odd);
-    if constexpr (FORCING != 0) {
-        const double cF = cdot<K>(m.fx, m.fy);
-        const double hw = 0.5 * p.w[K];
-        const double r = p.inv_cs_2 * cF;
-        if constexpr (FORCING == 1) {
-            half_phi[K] = hw * r;
-            half_phi[KI] = -(hw * r);
-        } else {
-            const double s = p.inv_cs_4 * (cu * cF) - p.inv_cs_2 * uF;
-            half_phi[K] = hw * (s + r);
-            half_phi[KI] = hw * (s - r);
-        }
+    constexpr int slot = (K == 1) ? 0 : (K == 2) ? 1 : (K == 5) ? 2 : 3;
+    static_assert(K == 1 || K == 2 || K == 5 || K == 8, "pair representative");
+    const double cu = cdot<K>(ux, uy);
+    double even, odd;
+    if constexpr (FORCING == 2) {
+        even = cu * (p.mrt.k4 * cu + p.mrt.k4cg[slot]) + base;
+    } else {
+        even = (p.mrt.k4 * cu) * cu + base;
     }
+    if constexpr (FORCING != 0) odd = p.inv_cs_2 * cu + p.mrt.k2cg[slot];
+    else odd = p.inv_cs_2 * cu;
+    g[K] = wrho * (even + odd) + proj;
+    g[KI] = wrho * (even - odd) + proj;
 }
 
 template <int FORCING>
-__device__ __forceinline__ void mrt_reduced_all(const KParams &p,
-                                                const Moments &m, double u2,
-                                                const double f[Q], double g[Q])
+__device__ __forceinline__ Moments collide_mrt_stress(const KParams &p,
+                                                      const double f[Q],
+                                                      double g[Q])
 {
-    double e[Q], half_phi[Q];
-    const double base = 1.0 - 0.5 * p.inv_cs_2 * u2;
-    const double uF = m.ux * m.fx + m.uy * m.fy;
-    e[0] = (p.w[0] * m.rho) * base;
-    half_phi[0] = (FORCING == 2) ? -(0.5 * p.w[0] * p.inv_cs_2) * uF : 0.0;
-    mrt_pair<1, FORCING>(p, m, base, uF, e, half_phi);
-    mrt_pair<2, FORCING>(p, m, base, uF, e, half_phi);
-    mrt_pair<5, FORCING>(p, m, base, uF, e, half_phi);
-    mrt_pair<8, FORCING>(p, m, base, uF, e, half_phi);
-    if constexpr (FORCING != 0) {
-#pragma unroll
-        for (int k = 0; k < Q; ++k) {
-            g[k] = e[k] + half_phi[k];      // feq + Phi/2
-            e[k] = e[k] - half_phi[k];      // so that h = f - e
-        }
+    // pair sums / differences shared by rho, the momentum and the stresses
+    const double p13 = f[1] + f[3], p24 = f[2] + f[4];
+    const double p57 = f[5] + f[7], p68 = f[6] + f[8];
+    const double d13 = f[1] - f[3], d24 = f[2] - f[4];
+    const double d57 = f[5] - f[7], d86 = f[8] - f[6];
+    Moments m;
+    m.rho = ((f[0] + p13) + p24) + (p57 + p68);
+    m.fx = m.rho * p.gx;
+    m.fy = m.rho * p.gy;
+    const double inv = 1.0 / (m.rho + p.eps);
+    // u = (sum_k c_k f_k + F/2) / rho, cpu/compute_fields_kernels.py:55-65
+    m.ux = (((d13 + d57) + d86) + m.rho * p.mrt.hgx) * inv;
+    m.uy = (((d24 + d57) - d86) + m.rho * p.mrt.hgy) * inv;
+    const double ux = m.ux, uy = m.uy;
+
+    double base, sa, sb;
+    if constexpr (FORCING == 2) {
+        base = 1.0 - p.mrt.k2 * ((ux * ux + uy * uy) + (ux * p.gx + uy * p.gy));
+        sa = ux * (ux - p.gx) - uy * (uy - p.gy);
+        sb = ux * (uy - p.mrt.hgy) - uy * p.mrt.hgx;
     } else {
-#pragma unroll
-        for (int k = 0; k < Q; ++k) g[k] = e[k];
+        base = 1.0 - p.mrt.k2 * (ux * ux + uy * uy);
+        sa = ux * ux - uy * uy;
+        sb = ux * uy;
     }
-    const double A = ((f[1] - e[1]) + (f[3] - e[3])) -
-                     ((f[2] - e[2]) + (f[4] - e[4]));
-    const double B = ((f[5] - e[5]) + (f[7] - e[7])) -
-                     ((f[6] - e[6]) + (f[8] - e[8]));
-    const double a = (0.25 * (1.0 - p.s[7])) * A;
-    const double b = (0.25 * (1.0 - p.s[8])) * B;
-    g[1] += a; g[3] += a; g[2] -= a; g[4] -= a;
-    g[5] += b; g[7] += b; g[6] -= b; g[8] -= b;
+    const double A = (p13 - p24) - (p.mrt.k7 * m.rho) * sa;
+    const double B = (p57 - p68) - (p.mrt.k8 * m.rho) * sb;
+    const double a = p.mrt.qa * A, b = p.mrt.qb * B;
+
+    const double w1rho = p.w[1] * m.rho, w5rho = p.w[5] * m.rho;
+    g[0] = (p.w[0] * m.rho) * base;
+    stress_pair<1, FORCING>(p, ux, uy, w1rho, base, a, g);
+    stress_pair<2, FORCING>(p, ux, uy, w1rho, base, -a, g);
+    stress_pair<5, FORCING>(p, ux, uy, w5rho, base, b, g);
+    stress_pair<8, FORCING>(p, ux, uy, w5rho, base, -b, g);
+    return m;
 }
 
 // Phases 2-5 for one node: moments, then post-collision populations g.
@@ -324,12 +309,15 @@ template <int COLL, int FORCING>
 __device__ __forceinline__ Moments collide(const KParams &p, const double f[Q],
                                            double g[Q])
 {
-    const Moments m = moments(p, f);
-    const double u2 = m.ux * m.ux + m.uy * m.uy;
-    if constexpr (COLL == 0) bgk_all<FORCING>(p, m, u2, f, g);
-    else if constexpr (COLL == 1) mrt_all<FORCING>(p, m, u2, f, g);
-    else mrt_reduced_all<FORCING>(p, m, u2, f, g);
-    return m;
+    if constexpr (COLL == 2) {
+        return collide_mrt_stress<FORCING>(p, f, g);
+    } else {
+        const Moments m = moments(p, f);
+        const double u2 = m.ux * m.ux + m.uy * m.uy;
+        if constexpr (COLL == 0) bgk_all<FORCING>(p, m, u2, f, g);
+        else mrt_all<FORCING>(p, m, u2, f, g);
+        return m;
+    }
 }
 
 }  // namespace plb

@@ -31,11 +31,23 @@ struct Layout {
 
 // Constants used verbatim by the kernels (values computed by the caller the
 // way the reference computes them, see plb_config in include/plb.h).
+// Derived constants of the two-stress-moment MRT path (collide_mrt_stress in
+// plb_collide.cuh), computed once on the host from the values above.
+struct MrtStress {
+    double hgx, hgy;     // g / 2
+    double k2, k4;       // 1 / (2 cs^2), 1 / (2 cs^4)
+    double k7, k8;       // w_1 / cs^4, 4 w_5 / cs^4
+    double qa, qb;       // (1 - s_7) / 4, (1 - s_8) / 4
+    double k4cg[4];      // k4 * (c . g) for c = (1,0), (0,1), (1,1), (1,-1)
+    double k2cg[4];      // k2 * (c . g)
+};
+
 struct KParams {
     Layout L;
     double omega, gx, gy, inv_cs_2, inv_cs_4, eps;
     double w[Q];
     double s[Q];   // MRT relaxation rates
+    MrtStress mrt;
 };
 
 // Node classes in the code plane.

@@ -49,7 +49,7 @@ __host__ __device__ constexpr int bulk_min_blocks(int coll, int forcing)
 #ifdef PLB_MINBLOCKS
     return PLB_MINBLOCKS;
 #else
-    return coll == 1 ? 4 : ((coll == 2 && forcing == 2) ? 5 : 6);
+    return coll == 1 ? 4 : 6;
 #endif
 }
 
