@@ -2,9 +2,8 @@
 
 Same flags as the reference; ``--backend`` gains (and defaults to) ``b200``,
 ``--toVTK`` (README spelling) is accepted for ``--to_vtk``.  Reconstruction and
-VTK conversion are the reference's own post-processing tools working on the
-unchanged .npz / metadata.json output; they are used if the reference package
-is importable and are otherwise reported as unavailable.
+VTK conversion (pylabolt_b200/postprocess.py) work on the unchanged .npz /
+metadata.json output, like the reference's own tools.
 """
 from argparse import ArgumentParser
 
@@ -40,18 +39,12 @@ def main(argv=None):
     elif args.solver is not None:
         raise SystemExit(f"solver {args.solver} is outside the b200 build "
                          "(fluidLB is the accelerated path)")
-    if args.reconstruct is not None or args.to_vtk is not None:
-        try:
-            if args.reconstruct is not None:
-                from pylabolt.utils.reconstruct import reconstruct_data
-                reconstruct_data(args.reconstruct, time_step=args.time)
-            if args.to_vtk is not None:
-                from pylabolt.utils.npz2vtk import convert_to_vtk
-                convert_to_vtk(args.to_vtk, args.time)
-        except ImportError as e:
-            raise SystemExit("post-processing uses the reference's own tools "
-                             "(pylabolt.utils.reconstruct / npz2vtk), which "
-                             f"are not importable here: {e}")
+    if args.reconstruct is not None:
+        from .postprocess import reconstruct_data
+        reconstruct_data(args.reconstruct, time_step=args.time)
+    if args.to_vtk is not None:
+        from .postprocess import convert_to_vtk
+        convert_to_vtk(args.to_vtk, args.time)
 
 
 if __name__ == "__main__":

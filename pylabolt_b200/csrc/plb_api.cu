@@ -113,8 +113,9 @@ struct plb_solver {
     int variant = 1;                 // 0 scalar, 1 vec2 (env PLB_KERNEL)
     int kernel_collision = 0;        // 0 BGK, 1 MRT (free rates), 2 MRT (reference rates)
 
-    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaStream_t stream = nullptr, comm_stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
+    cudaEvent_t ev_filled[2] = {}, ev_drained[2] = {};   // staging halves
     cudaEvent_t events[8] = {};
 
     double *f[2] = {nullptr, nullptr};   // two lattices, 9 planes each
@@ -158,84 +159,119 @@ struct plb_solver {
 
 namespace {
 
-int ensure_staging(plb_solver *s, size_t bytes)
+// Host <-> device transfers go through two staging halves so that the PCIe
+// copy of one chunk (copy stream) overlaps the layout transpose of the other
+// (main stream): reference layout (padded / inner, ncomp interleaved) on the
+// host side, planes on the device side.
+constexpr size_t CHUNK_BYTES = size_t(64) << 20;
+
+int ensure_staging(plb_solver *s, size_t half_bytes)
 {
-    if (s->staging_bytes >= bytes) return PLB_OK;
+    if (!s->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_filled[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_drained[i], cudaEventDisableTiming));
+        }
+    }
+    if (s->staging_bytes >= half_bytes) return PLB_OK;
     if (s->staging) CUDA_TRY(cudaFree(s->staging));
     s->staging = nullptr;
     s->staging_bytes = 0;
-    CUDA_TRY(cudaMalloc(&s->staging, bytes));
-    s->staging_bytes = bytes;
+    CUDA_TRY(cudaMalloc(&s->staging, 2 * half_bytes));
+    s->staging_bytes = half_bytes;
     return PLB_OK;
 }
 
-constexpr size_t CHUNK_BYTES = size_t(64) << 20;
-
-// reference layout (padded, ncomp interleaved) -> planes
-int upload_padded(plb_solver *s, const double *host, int ncomp, double *planes,
-                  int64_t plane_stride)
+// host rows [0, n_rows) of row_elems doubles -> unpack(staging, row0, nrows)
+template <typename Unpack>
+int upload_rows(plb_solver *s, const double *host, int64_t row_elems, int64_t n_rows,
+                Unpack unpack)
 {
-    const Layout &L = s->L;
-    const int64_t row_elems = (L.ny + 2) * ncomp;
     const int64_t rows_per_chunk =
         std::max<int64_t>(1, int64_t(CHUNK_BYTES / (row_elems * sizeof(double))));
-    if (int rc = ensure_staging(s, size_t(rows_per_chunk) * row_elems * sizeof(double)))
-        return rc;
-    for (int64_t row0 = 0; row0 < L.nx + 2; row0 += rows_per_chunk) {
-        const int64_t nrows = std::min(rows_per_chunk, L.nx + 2 - row0);
-        CUDA_TRY(cudaMemcpyAsync(s->staging, host + row0 * row_elems,
+    const size_t half = size_t(rows_per_chunk) * row_elems * sizeof(double);
+    if (int rc = ensure_staging(s, half)) return rc;
+    int64_t chunk = 0;
+    for (int64_t row0 = 0; row0 < n_rows; row0 += rows_per_chunk, ++chunk) {
+        const int h = int(chunk & 1);
+        double *stage = s->staging + h * (half / sizeof(double));
+        const int64_t nrows = std::min(rows_per_chunk, n_rows - row0);
+        if (chunk >= 2) CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->ev_drained[h], 0));
+        CUDA_TRY(cudaMemcpyAsync(stage, host + row0 * row_elems,
                                  size_t(nrows) * row_elems * sizeof(double),
-                                 cudaMemcpyHostToDevice, s->stream));
-        s->launches += launch_unpack_rows(L, s->staging, ncomp, planes,
-                                          plane_stride, row0, nrows, s->stream);
+                                 cudaMemcpyHostToDevice, s->copy_stream));
+        CUDA_TRY(cudaEventRecord(s->ev_filled[h], s->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_filled[h], 0));
+        s->launches += unpack(stage, row0, nrows);
+        CUDA_TRY(cudaEventRecord(s->ev_drained[h], s->stream));
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return PLB_OK;
 }
 
+// pack(staging, row0, nrows) -> host rows [0, n_rows) of row_elems doubles
+template <typename Pack>
+int download_rows(plb_solver *s, double *host, int64_t row_elems, int64_t n_rows,
+                  Pack pack)
+{
+    const int64_t rows_per_chunk =
+        std::max<int64_t>(1, int64_t(CHUNK_BYTES / (row_elems * sizeof(double))));
+    const size_t half = size_t(rows_per_chunk) * row_elems * sizeof(double);
+    if (int rc = ensure_staging(s, half)) return rc;
+    int64_t chunk = 0;
+    for (int64_t row0 = 0; row0 < n_rows; row0 += rows_per_chunk, ++chunk) {
+        const int h = int(chunk & 1);
+        double *stage = s->staging + h * (half / sizeof(double));
+        const int64_t nrows = std::min(rows_per_chunk, n_rows - row0);
+        if (chunk >= 2) CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_drained[h], 0));
+        s->launches += pack(stage, row0, nrows);
+        CUDA_TRY(cudaEventRecord(s->ev_filled[h], s->stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->ev_filled[h], 0));
+        CUDA_TRY(cudaMemcpyAsync(host + row0 * row_elems, stage,
+                                 size_t(nrows) * row_elems * sizeof(double),
+                                 cudaMemcpyDeviceToHost, s->copy_stream));
+        CUDA_TRY(cudaEventRecord(s->ev_drained[h], s->copy_stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return PLB_OK;
+}
+
+int upload_padded(plb_solver *s, const double *host, int ncomp, double *planes,
+                  int64_t plane_stride)
+{
+    const Layout &L = s->L;
+    return upload_rows(s, host, (L.ny + 2) * ncomp, L.nx + 2,
+                       [&](double *stage, int64_t row0, int64_t nrows) {
+                           return launch_unpack_rows(L, stage, ncomp, planes, plane_stride,
+                                                     row0, nrows, s->stream);
+                       });
+}
+
 int download_padded(plb_solver *s, double *host, int ncomp, const double *planes,
                     int64_t plane_stride, int zero_mode)
 {
     const Layout &L = s->L;
-    const int64_t row_elems = (L.ny + 2) * ncomp;
-    const int64_t rows_per_chunk =
-        std::max<int64_t>(1, int64_t(CHUNK_BYTES / (row_elems * sizeof(double))));
-    if (int rc = ensure_staging(s, size_t(rows_per_chunk) * row_elems * sizeof(double)))
-        return rc;
-    for (int64_t row0 = 0; row0 < L.nx + 2; row0 += rows_per_chunk) {
-        const int64_t nrows = std::min(rows_per_chunk, L.nx + 2 - row0);
-        s->launches += launch_pack_rows(L, s->staging, ncomp, planes, plane_stride,
-                                        row0, nrows, s->code, zero_mode, s->stream);
-        CUDA_TRY(cudaMemcpyAsync(host + row0 * row_elems, s->staging,
-                                 size_t(nrows) * row_elems * sizeof(double),
-                                 cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(cudaStreamSynchronize(s->stream));
-    }
-    CUDA_TRY(cudaGetLastError());
-    return PLB_OK;
+    return download_rows(s, host, (L.ny + 2) * ncomp, L.nx + 2,
+                         [&](double *stage, int64_t row0, int64_t nrows) {
+                             return launch_pack_rows(L, stage, ncomp, planes, plane_stride,
+                                                     row0, nrows, s->code, zero_mode,
+                                                     s->stream);
+                         });
 }
 
 int download_inner(plb_solver *s, double *host, int ncomp, const double *planes,
                    int64_t plane_stride)
 {
     const Layout &L = s->L;
-    const int64_t row_elems = L.ny * ncomp;
-    const int64_t rows_per_chunk =
-        std::max<int64_t>(1, int64_t(CHUNK_BYTES / (row_elems * sizeof(double))));
-    if (int rc = ensure_staging(s, size_t(rows_per_chunk) * row_elems * sizeof(double)))
-        return rc;
-    for (int64_t x0 = 0; x0 < L.nx; x0 += rows_per_chunk) {
-        const int64_t nrows = std::min(rows_per_chunk, L.nx - x0);
-        s->launches += launch_pack_inner(L, s->staging, ncomp, planes, plane_stride,
-                                         x0, nrows, s->stream);
-        CUDA_TRY(cudaMemcpyAsync(host + x0 * row_elems, s->staging,
-                                 size_t(nrows) * row_elems * sizeof(double),
-                                 cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(cudaStreamSynchronize(s->stream));
-    }
-    CUDA_TRY(cudaGetLastError());
-    return PLB_OK;
+    return download_rows(s, host, L.ny * ncomp, L.nx,
+                         [&](double *stage, int64_t x0, int64_t nrows) {
+                             return launch_pack_inner(L, stage, ncomp, planes, plane_stride,
+                                                      x0, nrows, s->stream);
+                         });
 }
 
 // Per-direction link codes of fluid node (x, y); see LinkCode.
@@ -537,6 +573,7 @@ void plb_destroy(plb_handle s)
     cudaSetDevice(s->cfg.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (int i = 0; i < 2; ++i) cudaFree(s->f[i]);
     cudaFree(s->mom);
@@ -557,6 +594,11 @@ void plb_destroy(plb_handle s)
     for (auto &e : s->events)
         if (e) cudaEventDestroy(e);
     for (auto &e : s->prof_events) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (s->ev_filled[i]) cudaEventDestroy(s->ev_filled[i]);
+        if (s->ev_drained[i]) cudaEventDestroy(s->ev_drained[i]);
+    }
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->ev_edge) cudaEventDestroy(s->ev_edge);
     if (s->ev_comm) cudaEventDestroy(s->ev_comm);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);

@@ -196,18 +196,46 @@ class InputOutputOperator:
         self.plb.upload(capi.POP, data["pop_fluid_new"])
         return True
 
+    def _pinned(self, name, shape):
+        """Page-locked download buffers, allocated (and faulted in) once and
+        reused by every output step."""
+        if not hasattr(self, "_pinned_buffers"):
+            self._pinned_buffers = {}
+        buf = self._pinned_buffers.get(name)
+        if buf is None:
+            if not hasattr(self.plb, "pinned"):
+                return None             # host stand-in of the I/O tests
+            buf = self.plb.pinned(shape)
+            buf.array[...] = 0.0
+            self._pinned_buffers[name] = buf
+        return buf.array
+
     def gather_fields(self, state):
-        """The arrays of one output file, ghost ring stripped."""
+        """The arrays of one output file, ghost ring stripped.  rho and u are
+        views of the reused pinned buffers (valid until the next call); the
+        flag fields of static bodies never change and are stripped once."""
         out = {}
+        n_inner = int(state.domain.inner_size)
+        if not hasattr(self, "_static_fields"):
+            self._static_fields = {}
         for name in self.fields_list:
             if name == "density":
-                out[name] = self.plb.download(capi.DENSITY_INNER)
+                out[name] = self.plb.download(
+                    capi.DENSITY_INNER, out=self._pinned(name, (n_inner,)))
             elif name == "velocity":
-                out[name] = self.plb.download(capi.VELOCITY_INNER)
+                out[name] = self.plb.download(
+                    capi.VELOCITY_INNER, out=self._pinned(name, (n_inner, 2)))
             else:
-                out[name] = strip_ghost(getattr(state.fields, name),
-                                        state.domain.shape)
+                if name not in self._static_fields:
+                    self._static_fields[name] = strip_ghost(
+                        getattr(state.fields, name), state.domain.shape)
+                out[name] = self._static_fields[name]
         return out
+
+    def close(self):
+        for buf in getattr(self, "_pinned_buffers", {}).values():
+            buf.free()
+        self._pinned_buffers = {}
 
     def write_fields(self, state, backend, time_step):
         interval = state.control.save_interval

@@ -269,6 +269,7 @@ class Solver:
                 "pop_fluid_new": self.plb.download(capi.POP)}
 
     def close(self):
+        self.io_operator.close()
         if self.plb is not None:
             self.plb.close()
             self.plb = None
