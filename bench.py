@@ -364,14 +364,16 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device):
     # roofline of the dominant kernel (bulk collide-stream), this rank
     peak, peak_src = hbm_peak()
     bulk_ms_per_step = bulk_ms / steps
-    achieved = (ALGORITHMIC_BYTES_PER_NODE * info["n_bulk"] /
+    achieved = (ALGORITHMIC_BYTES_PER_NODE * info["n_bulk_timed"] /
                 (bulk_ms_per_step * 1e-3) / 1e9)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(workload),
                 "kernel": "k_bulk_vec2" if info["variant"] else "k_bulk_scalar",
-                "algorithmic_bytes_per_step":
-                    ALGORITHMIC_BYTES_PER_NODE * info["n_bulk"],
+                "algorithmic_bytes_per_launch":
+                    ALGORITHMIC_BYTES_PER_NODE * info["n_bulk_timed"],
+                "face_transport": ["none", "own ghost rows", "nccl",
+                                   "p2p stores"][info["faces"]],
                 "launches_per_step": bulk_n / steps,
                 "kernel_ms_per_step": bulk_ms_per_step,
                 "kernel_share_of_step": bulk_ms / (ms * 1.0),

@@ -176,7 +176,12 @@ int plb_download_link_exchange(plb_handle h, double *out, int64_t n_values);
 int plb_comm_unique_id(void *id128);
 /* Joins the slab ring.  left_rank / right_rank are the ranks that own the
  * neighbouring slabs (-1 = none).  Replaces MPIOperator.find_neighbor_ranks
- * and halo_exchange, pylabolt/parallel/MPI_operator.py:116-259. */
+ * and halo_exchange, pylabolt/parallel/MPI_operator.py:116-259.
+ * Collective over all ranks.  The three populations that cross a face are
+ * stored by the kernels that produce them directly into the neighbour's
+ * receive buffer (CUDA IPC mapping over NVLink, mailbox hand-shake); if a
+ * neighbour cannot be mapped, or with PLB_FACE=nccl in the environment, they
+ * travel by ncclSend / ncclRecv instead. */
 int plb_comm_init(plb_handle h, const void *id128, int32_t rank,
                   int32_t n_ranks, int32_t left_rank, int32_t right_rank);
 
@@ -189,10 +194,16 @@ int plb_event_elapsed_ms(plb_handle h, int32_t start_slot, int32_t stop_slot,
 /* Per-kernel timing of the dominant (bulk collide-stream) kernel: while
  * enabled, every bulk launch is bracketed by CUDA events on the launching
  * stream.  plb_profile_read returns the summed duration and the number of
- * launches since the last read (it synchronises the events). */
+ * launches since the last read (it synchronises the events).  Only the
+ * dominant launch of a step is bracketed (all columns, or all but the two
+ * slab-edge columns when the slab has faces); plb_info reports how many bulk
+ * nodes it covers. */
 int plb_profile_enable(plb_handle h, int32_t enable);
 int plb_profile_read(plb_handle h, double *bulk_ms, int64_t *n_launches);
-/* out = {n_bulk, n_link, n_solid, pitch, plane, kernel_variant, 0, 0} */
+/* out = {n_bulk, n_link, n_solid, pitch, plane, kernel_variant,
+ *        bulk nodes of the profiled (dominant) bulk launch,
+ *        face transport: 0 none, 1 own ghost rows (single-rank periodic seam),
+ *                        2 NCCL send/recv, 3 peer-to-peer stores} */
 int plb_info(plb_handle h, int64_t out[8]);
 /* Kernels launched by this handle since creation / since the last reset. */
 int64_t plb_kernel_launches(plb_handle h, int32_t reset);

@@ -33,6 +33,8 @@ EXPORTS = [
     "plb_link_nodes", "plb_download_link_exchange",
 ]
 STORE_MOMENTS, RECORD_LINKS = 1, 2
+# plb_info()["faces"]: how the slab-face populations travel
+FACES_NONE, FACES_SELF, FACES_NCCL, FACES_P2P = range(4)
 
 
 class PlbConfig(ctypes.Structure):
@@ -316,8 +318,9 @@ class Plb:
     def info(self):
         out = (ctypes.c_int64 * 8)()
         self._check(self.lib.plb_info(self._h, out))
-        keys = ("n_bulk", "n_link", "n_solid", "pitch", "plane", "variant")
-        return dict(zip(keys, out[:6]))
+        keys = ("n_bulk", "n_link", "n_solid", "pitch", "plane", "variant",
+                "n_bulk_timed", "faces")
+        return dict(zip(keys, out[:8]))
 
     def flush_l2(self):
         self._check(self.lib.plb_flush_l2(self._h))

@@ -45,6 +45,8 @@ int fail(int code, const char *fmt, ...)
                         cudaGetErrorString(err__), __FILE__, __LINE__);       \
     } while (0)
 
+constexpr size_t XBUF_MAILBOX = 256;   // bytes reserved for the p2p mailbox words
+
 constexpr int CX[Q] = PLB_CX_LIST;
 constexpr int CY[Q] = PLB_CY_LIST;
 constexpr int INV[Q] = PLB_INV_LIST;
@@ -57,6 +59,7 @@ struct NcclApi {
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -81,6 +84,7 @@ int load_nccl()
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(Send, "ncclSend")
     SYM(Recv, "ncclRecv")
+    SYM(AllReduce, "ncclAllReduce")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -113,7 +117,7 @@ struct plb_solver {
     int variant = 1;                 // 0 scalar, 1 vec2 (env PLB_KERNEL)
     int kernel_collision = 0;        // 0 BGK, 1 MRT (free rates), 2 MRT (reference rates)
 
-    cudaStream_t stream = nullptr, comm_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, edge_stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
     cudaEvent_t ev_filled[2] = {}, ev_drained[2] = {};   // staging halves
     cudaEvent_t events[8] = {};
@@ -140,10 +144,19 @@ struct plb_solver {
     std::vector<std::pair<ZgLink *, int64_t>> zg_dev;
     uint8_t *mask_left = nullptr, *mask_right = nullptr;
     int64_t n_bulk = 0, n_solid = 0;
+    int64_t n_bulk_edge[2] = {0, 0};     // bulk nodes in columns 0 and nx - 1
 
     ncclComm_t comm = nullptr;
     int rank = 0, n_ranks = 1, left_rank = -1, right_rank = -1;
-    double *recv_left = nullptr, *recv_right = nullptr;   // 3 * ny each
+    double *recv_left = nullptr, *recv_right = nullptr;   // 3 * ny each (NCCL faces)
+
+    // Peer-to-peer faces (see setup_p2p): one exchange buffer per rank,
+    //   [mailbox: 32 x u64][recv_left: 2 x 3 x pitch doubles][recv_right: same]
+    // exported with CUDA IPC and mapped by both neighbours.
+    bool p2p = false;
+    unsigned char *xbuf = nullptr;
+    unsigned char *peer_left = nullptr, *peer_right = nullptr;   // their xbuf
+    long long spin_budget = 0;
 
     int64_t launches = 0;
     int64_t steps_done = 0;
@@ -338,11 +351,16 @@ int run_zero_gradient(plb_solver *s, double *fout, cudaStream_t st)
     return PLB_OK;
 }
 
+// Launches the bulk kernel on columns [x0, x1).  `timed`: the launch is the
+// dominant one of the step (main stream) and, while profiling is enabled, is
+// bracketed by CUDA events on its stream.  `edge`: a slab-edge column whose
+// face pushes go to the neighbour's memory (peer-to-peer faces).
 int bulk_timed(plb_solver *s, const StepArgs &a, int64_t x0, int64_t x1,
-               cudaStream_t stream)
+               cudaStream_t stream, bool timed, bool edge = false)
 {
     if (x1 <= x0) return PLB_OK;
-    if (s->profile) {
+    const bool prof = s->profile && timed;
+    if (prof) {
         if (s->prof_used + 2 > s->prof_events.size()) {
             for (int i = 0; i < 2; ++i) {
                 cudaEvent_t e;
@@ -352,8 +370,9 @@ int bulk_timed(plb_solver *s, const StepArgs &a, int64_t x0, int64_t x1,
         }
         CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used], stream));
     }
-    s->launches += launch_bulk(a, x0, x1, s->variant, stream);
-    if (s->profile) {
+    s->launches += edge ? launch_bulk_edge(a, x0, x1, stream)
+                        : launch_bulk(a, x0, x1, s->variant, stream);
+    if (prof) {
         CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used + 1], stream));
         s->prof_used += 2;
     }
@@ -384,76 +403,201 @@ int step_once(plb_solver *s, bool store, bool record)
     const int32_t right_dirs[3] = {1, 5, 8}, left_dirs[3] = {3, 6, 7};
     const bool faces = s->cfg.left_neighbor || s->cfg.right_neighbor;
 
+    // Two concurrent chains that write disjoint slots of lattice B.
+    //   edge stream (high priority): the O(perimeter) work -- with slab faces
+    //     the two edge columns first (they feed the faces), then the link
+    //     nodes, the face exchange (NCCL between ranks, this rank's own ghost
+    //     rows for a single-rank periodic seam) and its delivery;
+    //   main stream: the bulk kernel on all other columns.
+    // They join before the zero_gradient pass, so the small kernels and the
+    // exchange latency hide behind the bulk pass.
+    cudaStream_t es = s->edge_stream;
+    CUDA_TRY(cudaEventRecord(s->ev_edge, s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(es, s->ev_edge, 0));
+    // peer-to-peer faces: this step's parity selects the half of the
+    // neighbours' receive buffers that the edge kernels store into
+    const unsigned long long t = (unsigned long long)(s->steps_done + 1);
+    const int64_t half = 3 * L.pitch;                 // doubles per parity
+    const int64_t par_off = int64_t(t & 1) * half;
+    if (s->p2p) {
+        a.face_stride = L.pitch;
+        if (s->left_rank >= 0)       // the left neighbour's recv_right
+            a.face_lo = reinterpret_cast<double *>(s->peer_left + XBUF_MAILBOX) +
+                        2 * half + par_off;
+        if (s->right_rank >= 0)      // the right neighbour's recv_left
+            a.face_hi = reinterpret_cast<double *>(s->peer_right + XBUF_MAILBOX) +
+                        par_off;
+    }
+    int64_t x_lo = 0, x_hi = L.nx;
+    if (faces && L.nx > 2) {
+        if (int rc = bulk_timed(s, a, 0, 1, es, false, s->p2p)) return rc;
+        if (int rc = bulk_timed(s, a, L.nx - 1, L.nx, es, false, s->p2p)) return rc;
+        x_lo = 1;
+        x_hi = L.nx - 1;
+    } else if (faces) {
+        if (int rc = bulk_timed(s, a, 0, L.nx, es, true, s->p2p)) return rc;
+        x_lo = x_hi = 0;
+    }
+    s->launches += launch_links(a, s->links_dev, s->n_links, s->elements_dev, es);
     if (!s->comm) {
-        if (int rc = bulk_timed(s, a, 0, L.nx, s->stream)) return rc;
-        s->launches += launch_links(a, s->links_dev, s->n_links, s->elements_dev,
-                                    s->stream);
-        if (faces) {
-            // single rank: the periodic image is this rank's own ghost column
-            if (s->cfg.left_neighbor)
-                s->launches += launch_face_unpack(
-                    L, fout, 0, right_dirs, fout, 1 * L.plane + L.at(L.nx, 0),
-                    5 * L.plane + L.at(L.nx, 0), 8 * L.plane + L.at(L.nx, 0),
-                    s->mask_left, s->stream);
-            if (s->cfg.right_neighbor)
-                s->launches += launch_face_unpack(
-                    L, fout, L.nx - 1, left_dirs, fout, 3 * L.plane + L.at(-1, 0),
-                    6 * L.plane + L.at(-1, 0), 7 * L.plane + L.at(-1, 0),
-                    s->mask_right, s->stream);
-        }
-        run_zero_gradient(s, fout, s->stream);
+        // single rank: the periodic image is this rank's own ghost column
+        if (s->cfg.left_neighbor)
+            s->launches += launch_face_unpack(
+                L, fout, 0, right_dirs, fout, 1 * L.plane + L.at(L.nx, 0),
+                5 * L.plane + L.at(L.nx, 0), 8 * L.plane + L.at(L.nx, 0),
+                s->mask_left, es);
+        if (s->cfg.right_neighbor)
+            s->launches += launch_face_unpack(
+                L, fout, L.nx - 1, left_dirs, fout, 3 * L.plane + L.at(-1, 0),
+                6 * L.plane + L.at(-1, 0), 7 * L.plane + L.at(-1, 0),
+                s->mask_right, es);
+    } else if (s->p2p) {
+        // the stores are done (stream order): publish step t to the neighbours
+        // (mailbox word 0 = "data from your left", word 1 = "from your right")
+        auto mailbox = [](unsigned char *base, int word) {
+            return reinterpret_cast<unsigned long long *>(base) + word;
+        };
+        s->launches += launch_face_signal(
+            s->right_rank >= 0 ? mailbox(s->peer_right, 0) : nullptr,
+            s->left_rank >= 0 ? mailbox(s->peer_left, 1) : nullptr, t, es);
+        const double *mine = reinterpret_cast<const double *>(s->xbuf + XBUF_MAILBOX);
+        if (s->left_rank >= 0)
+            s->launches += launch_face_unpack(
+                L, fout, 0, right_dirs, mine + par_off, L.y0, L.pitch + L.y0,
+                2 * L.pitch + L.y0, s->mask_left, es, mailbox(s->xbuf, 0), t,
+                mailbox(s->xbuf, 2), s->spin_budget);
+        if (s->right_rank >= 0)
+            s->launches += launch_face_unpack(
+                L, fout, L.nx - 1, left_dirs, mine + 2 * half + par_off, L.y0,
+                L.pitch + L.y0, 2 * L.pitch + L.y0, s->mask_right, es,
+                mailbox(s->xbuf, 1), t, mailbox(s->xbuf, 2), s->spin_budget);
     } else {
-        // Two concurrent chains.  High-priority comm stream: the two slab-edge
-        // columns and the link nodes (everything that feeds a face), the face
-        // exchange and its delivery.  Main stream: the interior columns.  The
-        // chains write disjoint slots of lattice B; they join before the
-        // zero_gradient pass, so the O(perimeter) kernels and the exchange
-        // latency are hidden behind the interior pass.
-        cudaStream_t cs = s->comm_stream;
-        CUDA_TRY(cudaEventRecord(s->ev_edge, s->stream));
-        CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_edge, 0));
-        if (int rc = bulk_timed(s, a, 0, 1, cs)) return rc;
-        if (L.nx > 1)
-            if (int rc = bulk_timed(s, a, L.nx - 1, L.nx, cs)) return rc;
-        s->launches += launch_links(a, s->links_dev, s->n_links, s->elements_dev, cs);
         NCCL_TRY(g_nccl.GroupStart());
         if (s->right_rank >= 0)
             for (int j = 0; j < 3; ++j)
                 NCCL_TRY(g_nccl.Send(fout + right_dirs[j] * L.plane + L.at(L.nx, 0),
                                      size_t(L.ny), ncclDouble, s->right_rank,
-                                     s->comm, s->comm_stream));
+                                     s->comm, es));
         if (s->left_rank >= 0)
             for (int j = 0; j < 3; ++j)
                 NCCL_TRY(g_nccl.Send(fout + left_dirs[j] * L.plane + L.at(-1, 0),
                                      size_t(L.ny), ncclDouble, s->left_rank,
-                                     s->comm, s->comm_stream));
+                                     s->comm, es));
         if (s->left_rank >= 0)
             for (int j = 0; j < 3; ++j)
                 NCCL_TRY(g_nccl.Recv(s->recv_left + j * L.ny, size_t(L.ny),
-                                     ncclDouble, s->left_rank, s->comm,
-                                     s->comm_stream));
+                                     ncclDouble, s->left_rank, s->comm, es));
         if (s->right_rank >= 0)
             for (int j = 0; j < 3; ++j)
                 NCCL_TRY(g_nccl.Recv(s->recv_right + j * L.ny, size_t(L.ny),
-                                     ncclDouble, s->right_rank, s->comm,
-                                     s->comm_stream));
+                                     ncclDouble, s->right_rank, s->comm, es));
         NCCL_TRY(g_nccl.GroupEnd());
         if (s->left_rank >= 0)
             s->launches += launch_face_unpack(L, fout, 0, right_dirs, s->recv_left,
-                                              0, L.ny, 2 * L.ny, s->mask_left,
-                                              s->comm_stream);
+                                              0, L.ny, 2 * L.ny, s->mask_left, es);
         if (s->right_rank >= 0)
             s->launches += launch_face_unpack(L, fout, L.nx - 1, left_dirs,
                                               s->recv_right, 0, L.ny, 2 * L.ny,
-                                              s->mask_right, s->comm_stream);
-        CUDA_TRY(cudaEventRecord(s->ev_comm, s->comm_stream));
-        if (int rc = bulk_timed(s, a, 1, L.nx - 1, s->stream)) return rc;
-        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
-        run_zero_gradient(s, fout, s->stream);
+                                              s->mask_right, es);
     }
+    CUDA_TRY(cudaEventRecord(s->ev_comm, es));
+    a.face_lo = a.face_hi = nullptr;
+    if (int rc = bulk_timed(s, a, x_lo, x_hi, s->stream, true)) return rc;
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
+    run_zero_gradient(s, fout, s->stream);
     s->cur ^= 1;
     s->steps_done += 1;
     return PLB_OK;
+}
+
+// Peer-to-peer slab faces.  Every rank exports one exchange buffer with CUDA
+// IPC; the 64-byte handles travel to both neighbours over the (bootstrap) NCCL
+// communicator, each neighbour maps the buffer, and from then on a step moves
+// its face populations with plain stores over NVLink from the kernels that
+// produce them -- no pack, no NCCL call, no proxy thread on the step path.
+// The decision is collective: if any rank cannot map a neighbour, all ranks
+// keep the NCCL send/recv faces.
+struct Hello {
+    cudaIpcMemHandle_t handle;
+    int64_t ny, pitch;
+};
+
+int setup_p2p(plb_solver *s)
+{
+    const Layout &L = s->L;
+    const size_t bytes = std::max<size_t>(
+        XBUF_MAILBOX + size_t(12) * L.pitch * sizeof(double), size_t(2) << 20);
+    CUDA_TRY(cudaMalloc(&s->xbuf, bytes));
+    CUDA_TRY(cudaMemset(s->xbuf, 0, bytes));
+
+    Hello mine;
+    memset(&mine, 0, sizeof mine);
+    int ok = cudaIpcGetMemHandle(&mine.handle, s->xbuf) == cudaSuccess;
+    cudaGetLastError();
+    mine.ny = L.ny;
+    mine.pitch = L.pitch;
+
+    // hello[0] = mine, hello[1] = left neighbour's, hello[2] = right neighbour's
+    Hello *hello = nullptr;
+    CUDA_TRY(cudaMalloc(&hello, 3 * sizeof(Hello)));
+    CUDA_TRY(cudaMemset(hello, 0, 3 * sizeof(Hello)));
+    CUDA_TRY(cudaMemcpy(hello, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NCCL_TRY(g_nccl.GroupStart());
+    if (s->left_rank >= 0) {
+        NCCL_TRY(g_nccl.Send(hello, sizeof(Hello), ncclChar, s->left_rank, s->comm, s->stream));
+        NCCL_TRY(g_nccl.Recv(hello + 1, sizeof(Hello), ncclChar, s->left_rank, s->comm, s->stream));
+    }
+    if (s->right_rank >= 0) {
+        NCCL_TRY(g_nccl.Send(hello, sizeof(Hello), ncclChar, s->right_rank, s->comm, s->stream));
+        NCCL_TRY(g_nccl.Recv(hello + 2, sizeof(Hello), ncclChar, s->right_rank, s->comm, s->stream));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    Hello theirs[3];
+    CUDA_TRY(cudaMemcpy(theirs, hello, sizeof theirs, cudaMemcpyDeviceToHost));
+
+    auto map = [&](const Hello &h, unsigned char **out) {
+        if (h.ny != L.ny || h.pitch != L.pitch) return false;
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, h.handle, cudaIpcMemLazyEnablePeerAccess) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        *out = static_cast<unsigned char *>(ptr);
+        return true;
+    };
+    if (ok && s->left_rank >= 0) ok = map(theirs[1], &s->peer_left);
+    if (ok && s->right_rank >= 0) {
+        if (s->right_rank == s->left_rank) s->peer_right = s->peer_left;   // ring of two
+        else ok = map(theirs[2], &s->peer_right);
+    }
+
+    // collective decision: min over ranks of "everything mapped"
+    int *flag = reinterpret_cast<int *>(hello);
+    CUDA_TRY(cudaMemcpy(flag, &ok, sizeof ok, cudaMemcpyHostToDevice));
+    NCCL_TRY(g_nccl.AllReduce(flag, flag, 1, ncclInt, ncclMin, s->comm, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(&ok, flag, sizeof ok, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaFree(hello));
+    s->p2p = ok != 0;
+
+    double timeout_s = 120.0;
+    if (const char *v = getenv("PLB_P2P_TIMEOUT_S")) timeout_s = atof(v);
+    int khz = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, s->cfg.device));
+    s->spin_budget = (long long)(timeout_s * 1e3 * double(khz));
+    return PLB_OK;
+}
+
+void close_p2p(plb_solver *s)
+{
+    if (s->peer_left) cudaIpcCloseMemHandle(s->peer_left);
+    if (s->peer_right && s->peer_right != s->peer_left)
+        cudaIpcCloseMemHandle(s->peer_right);
+    s->peer_left = s->peer_right = nullptr;
+    cudaFree(s->xbuf);
+    s->xbuf = nullptr;
 }
 
 }  // namespace
@@ -550,6 +694,13 @@ int plb_create(const plb_config *c, plb_handle *out)
                                 cudaGetErrorString(err__)));                  \
     } while (0)
     TRY_OR_CLEAN(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        TRY_OR_CLEAN(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        TRY_OR_CLEAN(cudaStreamCreateWithPriority(&s->edge_stream, cudaStreamNonBlocking, hi));
+        TRY_OR_CLEAN(cudaEventCreateWithFlags(&s->ev_edge, cudaEventDisableTiming));
+        TRY_OR_CLEAN(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
+    }
     for (auto &e : s->events) TRY_OR_CLEAN(cudaEventCreate(&e));
     const size_t plane_bytes = size_t(L.plane) * sizeof(double);
     for (int i = 0; i < 2; ++i) {
@@ -572,8 +723,9 @@ void plb_destroy(plb_handle s)
     if (!s) return;
     cudaSetDevice(s->cfg.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
+    if (s->edge_stream) cudaStreamSynchronize(s->edge_stream);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    close_p2p(s);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (int i = 0; i < 2; ++i) cudaFree(s->f[i]);
     cudaFree(s->mom);
@@ -601,7 +753,7 @@ void plb_destroy(plb_handle s)
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->ev_edge) cudaEventDestroy(s->ev_edge);
     if (s->ev_comm) cudaEventDestroy(s->ev_comm);
-    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->edge_stream) cudaStreamDestroy(s->edge_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -701,6 +853,8 @@ int plb_finalize_geometry(plb_handle s)
             if (lk == 0) {
                 crow[y] = NODE_BULK;
                 ++n_bulk;
+                if (x == 0) ++s->n_bulk_edge[0];
+                if (x == nx - 1 && nx > 1) ++s->n_bulk_edge[1];
             } else {
                 crow[y] = NODE_LINK;
                 link_nodes.push_back(LinkNode{int32_t(x), int32_t(y), lk});
@@ -901,8 +1055,16 @@ int plb_sync(plb_handle s)
 {
     if (!s) return fail(PLB_ERR_INVALID, "null handle");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
-    if (s->comm_stream) CUDA_TRY(cudaStreamSynchronize(s->comm_stream));
+    CUDA_TRY(cudaStreamSynchronize(s->edge_stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->p2p) {
+        unsigned long long status = 0;
+        CUDA_TRY(cudaMemcpy(&status, s->xbuf + 2 * sizeof status, sizeof status,
+                            cudaMemcpyDeviceToHost));
+        if (status)
+            return fail(PLB_ERR_NCCL, "slab-face exchange timed out: a neighbour "
+                        "rank never published its step (PLB_P2P_TIMEOUT_S)");
+    }
     return PLB_OK;
 }
 
@@ -962,13 +1124,13 @@ int plb_comm_init(plb_handle s, const void *id128, int32_t rank, int32_t n_ranks
     s->n_ranks = n_ranks;
     s->left_rank = left_rank;
     s->right_rank = right_rank;
-    int lo = 0, hi = 0;
-    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CUDA_TRY(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, hi));
-    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_edge, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&s->recv_left, size_t(3 * s->L.ny) * sizeof(double)));
     CUDA_TRY(cudaMalloc(&s->recv_right, size_t(3 * s->L.ny) * sizeof(double)));
+    // face transport: peer-to-peer stores unless PLB_FACE=nccl (A/B runs) or a
+    // neighbour cannot be mapped
+    const char *mode = getenv("PLB_FACE");
+    if (!(mode && strcmp(mode, "nccl") == 0))
+        if (int rc = setup_p2p(s)) return rc;
     return PLB_OK;
 }
 
@@ -1024,7 +1186,13 @@ int plb_info(plb_handle s, int64_t out[8])
     out[3] = s->L.pitch;
     out[4] = s->L.plane;
     out[5] = s->variant;
-    out[6] = out[7] = 0;
+    // bulk nodes of the dominant (profiled) launch, and the face transport:
+    // 0 none, 1 this rank's own ghost rows (periodic seam), 2 NCCL, 3 p2p
+    const bool faces = s->cfg.left_neighbor || s->cfg.right_neighbor;
+    out[6] = (faces && s->L.nx > 2)
+                 ? s->n_bulk - s->n_bulk_edge[0] - s->n_bulk_edge[1]
+                 : s->n_bulk;
+    out[7] = !faces ? 0 : (!s->comm ? 1 : (s->p2p ? 3 : 2));
     return PLB_OK;
 }
 

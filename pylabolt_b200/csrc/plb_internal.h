@@ -99,14 +99,27 @@ struct StepArgs {
     double *rho, *ux, *uy;   // moment planes (ux/uy also hold solid velocities)
     double *exch;            // per link node x 8: momentum exchange, or null
     int32_t collision, forcing, store;
+    // Peer-to-peer slab faces: where the ghost row x = -1 (populations 3, 6, 7)
+    // and x = nx (populations 1, 5, 8) live -- three rows `face_stride` apart
+    // in the NEIGHBOUR RANK's receive buffer, written directly over NVLink by
+    // the edge-column and link kernels.  Null: this rank's own ghost rows.
+    double *face_lo = nullptr, *face_hi = nullptr;
+    int64_t face_stride = 0;
 };
 
 // ---- launchers implemented in plb_kernels.cu ---------------------------
 // All return the number of kernels launched (0 if nothing to do).
 int launch_bulk(const StepArgs &a, int64_t x_begin, int64_t x_end, int variant,
                 cudaStream_t stream);
+// One slab-edge column with the face redirection of StepArgs::face_lo/hi.
+int launch_bulk_edge(const StepArgs &a, int64_t x_begin, int64_t x_end,
+                     cudaStream_t stream);
 int launch_links(const StepArgs &a, const LinkNode *nodes, int64_t n_nodes,
                  const ElementDev *elements, cudaStream_t stream);
+// Peer-to-peer face hand-shake: publishes `value` in the neighbours' mailboxes
+// (either pointer may be null).
+int launch_face_signal(unsigned long long *flag_a, unsigned long long *flag_b,
+                       unsigned long long value, cudaStream_t stream);
 int launch_zero_gradient(double *fout, int64_t plane, const ZgLink *links,
                          int64_t n_links, cudaStream_t stream);
 // Copies the three face populations from `src` (three rows of ny doubles,
@@ -115,7 +128,11 @@ int launch_face_unpack(const Layout &L, double *fout, int64_t x_col,
                        const int32_t dirs[3], const double *src,
                        int64_t src_stride0, int64_t src_stride1,
                        int64_t src_stride2, const uint8_t *mask,
-                       cudaStream_t stream);
+                       cudaStream_t stream,
+                       const unsigned long long *wait_flag = nullptr,
+                       unsigned long long wait_value = 0,
+                       unsigned long long *status = nullptr,
+                       long long spin_budget = 0);
 int launch_init_pop(const KParams &p, double *f, const uint8_t *code,
                     const double *rho, const double *ux, const double *uy,
                     cudaStream_t stream);

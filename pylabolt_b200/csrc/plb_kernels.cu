@@ -118,6 +118,50 @@ k_bulk_scalar(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
 }
 
 // ---------------------------------------------------------------------------
+// slab-edge columns with peer-to-peer faces
+// ---------------------------------------------------------------------------
+// Where population q pushed to (tx, ty) lands: a ghost row that stands for the
+// neighbouring slab is redirected into that rank's receive buffer (peer memory
+// mapped over NVLink), everything else is the local lattice.
+__device__ __forceinline__ double *push_dst(const StepArgs &a, int q, int64_t tx,
+                                            int64_t ty)
+{
+    const Layout &L = a.p.L;
+    // populations 1, 5, 8 cross the right face, 3, 6, 7 the left one
+    const int slot = (q == 1 || q == 3) ? 0 : ((q == 5 || q == 6) ? 1 : 2);
+    if (tx < 0 && a.face_lo)
+        return a.face_lo + slot * a.face_stride + L.y0 + ty;
+    if (tx >= L.nx && a.face_hi)
+        return a.face_hi + slot * a.face_stride + L.y0 + ty;
+    return a.fout + q * L.plane + L.at(tx, ty);
+}
+
+template <int COLL, int FORCING, bool STORE>
+__global__ void __launch_bounds__(256)
+k_bulk_edge(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
+{
+    const int64_t row = blockIdx.x / chunks_per_row;
+    const int32_t chunk = blockIdx.x - row * chunks_per_row;
+    const int64_t y = int64_t(chunk) * 256 + threadIdx.x;
+    if (y >= a.p.L.ny) return;
+    const int64_t x = x_begin + row;
+    const int64_t idx = a.p.L.at(x, y);
+    if (a.code[idx] != NODE_BULK) return;
+    double f[Q], g[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) f[k] = a.fin[k * a.p.L.plane + idx];
+    const Moments m = collide<COLL, FORCING>(a.p, f, g);
+    if constexpr (STORE) {
+        a.rho[idx] = m.rho;
+        a.ux[idx] = m.ux;
+        a.uy[idx] = m.uy;
+    }
+#pragma unroll
+    for (int k = 0; k < Q; ++k)
+        *push_dst(a, k, x + d_cx[k], y + d_cy[k]) = g[k];
+}
+
+// ---------------------------------------------------------------------------
 // two nodes per thread, 128-bit loads and stores
 // ---------------------------------------------------------------------------
 // A warp owns 64 consecutive y of one row.  Loads are aligned double2.  The
@@ -242,13 +286,13 @@ k_links(StepArgs a, const LinkNode *__restrict__ nodes, int64_t n_nodes,
         bool own = true;      // this node writes its own slot f'[i, inv q]
         double back = 0.0;    // ... with this value
         if (code == LINK_PUSH) {
-            a.fout[q * plane + idx + cx * pitch + cy] = g[q];
+            *push_dst(a, q, nd.x + cx, nd.y + cy) = g[q];
             own = false;
         } else if (code == LINK_WRAP) {
             int64_t ty = nd.y + cy;
             if (ty < 0) ty = L.ny - 1;
             else if (ty >= L.ny) ty = 0;
-            a.fout[q * plane + L.at(nd.x + cx, ty)] = g[q];
+            *push_dst(a, q, nd.x + cx, ty) = g[q];
             own = false;
         } else if (code == LINK_SOLID_BB) {
             // cpu/streaming_kernels.py:40-47 (k_inv = q, ind_nb = target)
@@ -304,21 +348,62 @@ __global__ void k_zero_gradient(double *fout, int64_t plane,
     fout[l.v * plane + l.dst] = fout[l.v * plane + l.src];
 }
 
+// Peer-to-peer hand-shake.  The edge-column and link kernels of step t have
+// stored this rank's outgoing face populations into the neighbours' receive
+// buffers; those kernels have completed (stream order), so their stores have
+// been performed and publishing the step number releases them.
+__global__ void k_face_signal(unsigned long long *flag_a,
+                              unsigned long long *flag_b,
+                              unsigned long long value)
+{
+    __threadfence_system();
+    if (flag_a) *reinterpret_cast<volatile unsigned long long *>(flag_a) = value;
+    if (flag_b) *reinterpret_cast<volatile unsigned long long *>(flag_b) = value;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(
+    const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p)
+                 : "memory");
+    return v;
+}
+
 // Delivery of the three populations that crossed a slab face (or the
-// periodic-x seam) into the first / last interior column.
+// periodic-x seam) into the first / last interior column.  With peer-to-peer
+// faces every CTA first waits until the neighbour has published step
+// `wait_value` in this rank's mailbox; a neighbour that never arrives sets
+// *status after `spin_budget` clock cycles instead of hanging the GPU.
 __global__ void k_face_unpack(Layout L, double *fout, int64_t x_col, int32_t k0,
                               int32_t k1, int32_t k2,
                               const double *__restrict__ src, int64_t s0,
                               int64_t s1, int64_t s2,
-                              const uint8_t *__restrict__ mask)
+                              const uint8_t *__restrict__ mask,
+                              const unsigned long long *wait_flag,
+                              unsigned long long wait_value,
+                              unsigned long long *status, long long spin_budget)
 {
+    if (wait_flag) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys(wait_flag) < wait_value) {
+                if (clock64() - t0 > spin_budget) {
+                    atomicExch(status, 1ull);
+                    break;
+                }
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+    }
     const int64_t y = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (y >= L.ny) return;
     const uint8_t mk = mask[y];
     const int64_t idx = L.at(x_col, y);
-    if (mk & 1) fout[k0 * L.plane + idx] = src[s0 + y];
-    if (mk & 2) fout[k1 * L.plane + idx] = src[s1 + y];
-    if (mk & 4) fout[k2 * L.plane + idx] = src[s2 + y];
+    if (mk & 1) fout[k0 * L.plane + idx] = __ldcg(src + s0 + y);
+    if (mk & 2) fout[k1 * L.plane + idx] = __ldcg(src + s1 + y);
+    if (mk & 4) fout[k2 * L.plane + idx] = __ldcg(src + s2 + y);
 }
 
 // ---------------------------------------------------------------------------
@@ -499,6 +584,17 @@ struct BulkVec2 {
 };
 
 template <int C, int F, bool S>
+struct BulkEdge {
+    static void run(const StepArgs &a, int64_t x_begin, int64_t n_rows,
+                    cudaStream_t st)
+    {
+        const int32_t chunks = int32_t((a.p.L.ny + 255) / 256);
+        k_bulk_edge<C, F, S><<<unsigned(n_rows * chunks), 256, 0, st>>>(
+            a, x_begin, chunks);
+    }
+};
+
+template <int C, int F, bool S>
 struct Links {
     static void run(const StepArgs &a, const LinkNode *nodes, int64_t n,
                     const ElementDev *el, cudaStream_t st)
@@ -519,6 +615,23 @@ int launch_bulk(const StepArgs &a, int64_t x_begin, int64_t x_end, int variant,
     else
         dispatch<BulkVec2>(a.collision, a.forcing, a.store != 0, a, x_begin,
                            n_rows, stream);
+    return 1;
+}
+
+int launch_bulk_edge(const StepArgs &a, int64_t x_begin, int64_t x_end,
+                     cudaStream_t stream)
+{
+    const int64_t n_rows = x_end - x_begin;
+    if (n_rows <= 0) return 0;
+    dispatch<BulkEdge>(a.collision, a.forcing, a.store != 0, a, x_begin, n_rows,
+                       stream);
+    return 1;
+}
+
+int launch_face_signal(unsigned long long *flag_a, unsigned long long *flag_b,
+                       unsigned long long value, cudaStream_t stream)
+{
+    k_face_signal<<<1, 1, 0, stream>>>(flag_a, flag_b, value);
     return 1;
 }
 
@@ -544,11 +657,14 @@ int launch_face_unpack(const Layout &L, double *fout, int64_t x_col,
                        const int32_t dirs[3], const double *src,
                        int64_t src_stride0, int64_t src_stride1,
                        int64_t src_stride2, const uint8_t *mask,
-                       cudaStream_t stream)
+                       cudaStream_t stream, const unsigned long long *wait_flag,
+                       unsigned long long wait_value, unsigned long long *status,
+                       long long spin_budget)
 {
     k_face_unpack<<<unsigned((L.ny + 255) / 256), 256, 0, stream>>>(
         L, fout, x_col, dirs[0], dirs[1], dirs[2], src, src_stride0,
-        src_stride1, src_stride2, mask);
+        src_stride1, src_stride2, mask, wait_flag, wait_value, status,
+        spin_budget);
     return 1;
 }
 

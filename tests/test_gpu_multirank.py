@@ -1,7 +1,14 @@
-"""x-slab decomposition across GPUs (one process per GPU, NCCL face exchange
-inside libplb) against the CPU oracle on the undecomposed domain.  Needs at
-least two GPUs: `gpurun --gpus 2 -- python -m pytest tests -m gpu -k multirank`.
+"""x-slab decomposition across GPUs (one process per GPU) against the CPU
+oracle on the undecomposed domain, with both face transports of libplb:
+peer-to-peer stores over NVLink (the default) and NCCL send/recv
+(PLB_FACE=nccl).  Needs at least two GPUs:
+`gpurun --gpus 2 -- python -m pytest tests -m gpu -k multirank`.
+
+All cases of one world size run inside ONE torchrun launch (process start-up
+and NCCL initialisation dominate a case); each test then looks up its own
+result.
 """
+import json
 import os
 import subprocess
 import sys
@@ -25,29 +32,55 @@ def _gpu_count():
 
 N_GPUS = _gpu_count()
 
+NAMES = ["cavity", "poiseuille", "cylinder_cut", "periodic_box", "mrt_box",
+         "spin"]
+# every case on both transports; the strict (bit-exact) build on the default
+# transport, plus two long runs that give a missed hand-shake time to show
+TWO_SLABS = ([f"{n}:25:strict:p2p" for n in NAMES] +
+             [f"{n}:25:production:nccl" for n in NAMES] +
+             ["periodic_box:25:production:p2p", "cylinder_cut:25:strict:nccl",
+              "periodic_box:400:strict:p2p", "poiseuille:400:strict:nccl"])
+FOUR_SLABS = ([f"{n}:25:strict:p2p" for n in
+               ("poiseuille", "cylinder_cut", "periodic_box")] +
+              ["periodic_box:25:strict:nccl", "mrt_box:300:production:p2p"])
 
-def run_case(name, world, steps, mode, port):
+
+def _launch(world, specs, port):
     with tempfile.TemporaryDirectory() as tmp:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                "--master-port", str(port),
-               os.path.join(HERE, "multirank_worker.py"), name, str(steps),
-               mode, tmp]
-        proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-        print(proc.stdout[-3000:])
-        print(proc.stderr[-3000:])
-        return proc.returncode
+               os.path.join(HERE, "multirank_worker.py"), tmp] + specs
+        env = dict(os.environ, PLB_P2P_TIMEOUT_S="20")
+        proc = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
+                              env=env)
+        log = proc.stdout[-6000:] + "\n" + proc.stderr[-3000:]
+        try:
+            with open(os.path.join(tmp, "results.json")) as f:
+                return json.load(f), log
+        except OSError:
+            return {}, log
+
+
+@pytest.fixture(scope="module")
+def two_slabs():
+    return _launch(2, TWO_SLABS, 29641)
+
+
+@pytest.fixture(scope="module")
+def four_slabs():
+    return _launch(4, FOUR_SLABS, 29642)
 
 
 @pytest.mark.skipif(N_GPUS < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("mode", ["strict", "production"])
-@pytest.mark.parametrize("name", ["cavity", "poiseuille", "cylinder_cut",
-                                  "periodic_box", "mrt_box", "spin"])
-def test_two_slabs_match_oracle(name, mode):
-    assert run_case(name, 2, 25, mode, 29641) == 0
+@pytest.mark.parametrize("spec", TWO_SLABS)
+def test_two_slabs_match_oracle(two_slabs, spec):
+    results, log = two_slabs
+    assert results.get(spec) == 0, log
 
 
 @pytest.mark.skipif(N_GPUS < 4, reason="needs >= 4 GPUs")
-@pytest.mark.parametrize("name", ["poiseuille", "cylinder_cut", "periodic_box"])
-def test_four_slabs_match_oracle(name):
-    assert run_case(name, 4, 25, "strict", 29642) == 0
+@pytest.mark.parametrize("spec", FOUR_SLABS)
+def test_four_slabs_match_oracle(four_slabs, spec):
+    results, log = four_slabs
+    assert results.get(spec) == 0, log
