@@ -486,7 +486,7 @@ def main():
             "roofline": cav["roofline"], "e2e": cav["e2e"]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = time_cpu_port(args.workload, 10, 2)
+        cpu = time_cpu_port(args.workload, 200, 2, budget_s=15.0, sample=4096)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
         line = {

@@ -37,6 +37,18 @@ namespace plb {
 #ifndef PLB_BLOCK
 #define PLB_BLOCK 128
 #endif
+// Issue the population loads before the node-code check (see k_bulk_vec2).
+// Measured on B200 (profiles/r01_occupancy_sweep.txt): +1 % (BGK) to +3.7 %
+// (BGK + Guo) for the reference-ordered BGK kernels, -0.3 .. -1.7 % for the
+// two-stress-moment MRT, hence per collision model.
+__host__ __device__ constexpr bool bulk_speculate(int coll)
+{
+#ifdef PLB_SPECULATE
+    return PLB_SPECULATE != 0;
+#else
+    return coll == 0;
+#endif
+}
 
 // Resident CTAs per SM requested from ptxas for the 128-bit bulk kernel.  The
 // kernel is latency bound on HBM: what matters is bytes in flight per SM, i.e.
@@ -188,6 +200,23 @@ k_bulk_vec2(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
     else if (y < L.ny)
         codes = uint16_t(a.code[idx]) | 0x0300;
 
+    const int64_t plane = L.plane, pitch = L.pitch;
+    double fa[Q], fb[Q], ga[Q], gb[Q];
+    // Speculative variant: the population loads do not wait for the code
+    // byte.  Any pair inside the padded row is a valid address, so they are
+    // issued together with the code load and one DRAM round trip leaves the
+    // critical path.  (Threads past the row end hold no bulk node; their warp
+    // takes the scalar path.)
+    if constexpr (bulk_speculate(COLL)) {
+        if (L.y0 + y + 1 < pitch) {
+#pragma unroll
+            for (int k = 0; k < Q; ++k) {
+                const double2 v = ld2(a.fin + k * plane + idx);
+                fa[k] = v.x;
+                fb[k] = v.y;
+            }
+        }
+    }
     if (!__all_sync(0xffffffffu, codes == 0)) {
         if ((codes & 0xff) == NODE_BULK)
             bulk_node<COLL, FORCING, STORE>(a, idx);
@@ -195,14 +224,13 @@ k_bulk_vec2(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
             bulk_node<COLL, FORCING, STORE>(a, idx + 1);
         return;
     }
-
-    const int64_t plane = L.plane, pitch = L.pitch;
-    double fa[Q], fb[Q], ga[Q], gb[Q];
+    if constexpr (!bulk_speculate(COLL)) {
 #pragma unroll
-    for (int k = 0; k < Q; ++k) {
-        const double2 v = ld2(a.fin + k * plane + idx);
-        fa[k] = v.x;
-        fb[k] = v.y;
+        for (int k = 0; k < Q; ++k) {
+            const double2 v = ld2(a.fin + k * plane + idx);
+            fa[k] = v.x;
+            fb[k] = v.y;
+        }
     }
     const Moments ma = collide<COLL, FORCING>(a.p, fa, ga);
     const Moments mb = collide<COLL, FORCING>(a.p, fb, gb);
