@@ -413,7 +413,9 @@ __global__ void k_face_unpack(Layout L, double *fout, int64_t x_col, int32_t k0,
                               unsigned long long *status, long long spin_budget)
 {
     if (wait_flag) {
-        if (threadIdx.x == 0) {
+        // a time-out is sticky: later steps do not wait again, plb_sync reports
+        if (threadIdx.x == 0 &&
+            *reinterpret_cast<volatile unsigned long long *>(status) == 0) {
             const long long t0 = clock64();
             while (ld_acquire_sys(wait_flag) < wait_value) {
                 if (clock64() - t0 > spin_budget) {
