@@ -205,3 +205,69 @@ def test_error_reporting():
             p.upload(capi.DENSITY, np.zeros(3))
     finally:
         p.close()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json configs[0..2] at their stated sizes, N in {1, 10, 1000} steps
+# ("Config 1-3")
+# ---------------------------------------------------------------------------
+def _poiseuille_re100(forcing):
+    """Gravity-driven plane Poiseuille flow at Re = u_max H / nu = 100:
+    128 x 65, nu = 0.064, g = 8 nu u_max / H^2, from rest."""
+    nu, height = 0.064, 65
+    u_max = 100.0 * nu / height
+    sim = cases.poiseuille(128, 65, end_time=1000, forcing=forcing,
+                           g=8.0 * nu * u_max / height ** 2, kin_visc=nu,
+                           perturb=0.0)
+    return sim
+
+
+def _cylinder_re100(model, outlet=None):
+    """Flow past a cylinder, Re = u D / nu = 0.05 * 20 / 0.01 = 100: static
+    circle, anti-bounce-back pressure inlet / outlet (or zero_gradient
+    outlet), bounce_back plates."""
+    sim = cases.cylinder(240, 101, end_time=1000, model=model, radius=10,
+                         rho_in=1.002, rho_out=0.998)
+    sim.transport_dict["kin_visc"] = 0.01
+    sim.initial_fields_dict["default"]["fluid"]["velocity"]["value"] = [0.05, 0.0]
+    if outlet is not None:
+        sim.boundary_dict["outlet"]["fluid"] = {"type": outlet}
+    return sim
+
+
+BASELINE_CONFIGS = {
+    # name: (factory, bit-exact in the strict build)
+    "config0_cavity_re100_bgk": (lambda: cases.cavity(101, 101, end_time=1000),
+                                 True),
+    "config1_poiseuille_re100_guo_linear":
+        (lambda: _poiseuille_re100("guo_linear"), True),
+    "config1_poiseuille_re100_guo_second_order":
+        (lambda: _poiseuille_re100("guo_second_order"), True),
+    "config2_cylinder_re100_bgk": (lambda: _cylinder_re100("BGK"), True),
+    "config2_cylinder_re100_mrt": (lambda: _cylinder_re100("MRT"), False),
+    "config2_cylinder_re100_mrt_zero_gradient":
+        (lambda: _cylinder_re100("MRT", outlet="zero_gradient"), False),
+}
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("name", sorted(BASELINE_CONFIGS))
+def test_baseline_configs_1_10_1000_steps(name, strict):
+    factory, bit_exact = BASELINE_CONFIGS[name]
+    s = make_solver(factory(), strict=strict)
+    try:
+        orc = oracle_for(s, n_threads=8)
+        done = 0
+        for n in (1, 10, 1000):
+            s.advance(n - done, store_moments_last=True)
+            orc.step(n - done)
+            done = n
+            got = s.fields_to_host()
+            for key, want in (("density", orc.density),
+                              ("velocity", orc.velocity),
+                              ("pop_fluid_new", orc.pop_new)):
+                assert rel_err(got[key], want) <= RTOL, (n, key)
+                if strict and bit_exact:
+                    assert np.array_equal(got[key], want), (n, key)
+    finally:
+        s.close()

@@ -12,7 +12,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $out/${tag}_launches_channel_mrt.csv \
     python bench.py --steps 3 --warmup 3 --no-extras --no-cpu-baseline > $out/${tag}_ncu_bench.log 2>&1
 for wl in channel cavity; do
-  ncu --set full --clock-control none --import-source on -k regex:k_bulk -s 3 -c 2 \
+  # the channel step launches the bulk kernel three times (two slab-edge
+  # columns, then the dominant interior launch): capture an interior one
+  skip=3; [ $wl = channel ] && skip=8
+  ncu --set full --clock-control none --import-source on -k regex:k_bulk -s $skip -c 1 \
       -f -o $out/${tag}_ncu_${wl} \
       python bench.py --workload $wl --steps 3 --warmup 3 --no-extras --no-cpu-baseline >> $out/${tag}_ncu_bench.log 2>&1
   ncu -i $out/${tag}_ncu_${wl}.ncu-rep --page raw --csv > $out/${tag}_ncu_raw_${wl}.csv 2>/dev/null
