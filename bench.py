@@ -332,6 +332,8 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device):
     plb = solver.plb
     info = plb.info()
 
+    copy_gbs = plb.copy_bandwidth()       # context for the roofline fraction
+
     # ---- device-resident throughput -------------------------------------
     sampler = ClockSampler(device)
     sampler.start()
@@ -377,7 +379,8 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device):
                 "launches_per_step": bulk_n / steps,
                 "kernel_ms_per_step": bulk_ms_per_step,
                 "kernel_share_of_step": bulk_ms / (ms * 1.0),
-                "peak_source": peak_src}
+                "peak_source": peak_src,
+                "d2d_copy_gbs_this_box": copy_gbs}
 
     # ---- end to end through the public Solver API, host buffers -----------
     size = plb.size

@@ -212,6 +212,10 @@ int plb_host_alloc(void **ptr, size_t bytes);
 int plb_host_free(void *ptr);
 /* Writes a scratch buffer larger than L2 (bench hygiene). */
 int plb_flush_l2(plb_handle h);
+/* Device-to-device copy rate of this GPU right now, in GB/s (read + write
+ * bytes of a 1 GiB cudaMemcpyAsync, best of 5): the practical HBM ceiling
+ * next to which a roofline fraction is read. */
+int plb_copy_bandwidth(plb_handle h, double *gbs);
 
 #ifdef __cplusplus
 }

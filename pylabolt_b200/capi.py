@@ -30,7 +30,7 @@ EXPORTS = [
     "plb_event_record", "plb_event_elapsed_ms", "plb_kernel_launches",
     "plb_host_alloc", "plb_host_free", "plb_flush_l2",
     "plb_profile_enable", "plb_profile_read", "plb_info",
-    "plb_link_nodes", "plb_download_link_exchange",
+    "plb_link_nodes", "plb_download_link_exchange", "plb_copy_bandwidth",
 ]
 STORE_MOMENTS, RECORD_LINKS = 1, 2
 # plb_info()["faces"]: how the slab-face populations travel
@@ -106,6 +106,7 @@ def load_library(strict=None):
     lib.plb_link_nodes.argtypes = [vp, ctypes.POINTER(i64), i64,
                                    ctypes.POINTER(i64)]
     lib.plb_download_link_exchange.argtypes = [vp, ctypes.POINTER(dbl), i64]
+    lib.plb_copy_bandwidth.argtypes = [vp, ctypes.POINTER(dbl)]
     _libs[strict] = lib
     return lib
 
@@ -321,6 +322,12 @@ class Plb:
         keys = ("n_bulk", "n_link", "n_solid", "pitch", "plane", "variant",
                 "n_bulk_timed", "faces")
         return dict(zip(keys, out[:8]))
+
+    def copy_bandwidth(self):
+        """GB/s (read + write) of a device-to-device copy on this GPU, now."""
+        gbs = ctypes.c_double()
+        self._check(self.lib.plb_copy_bandwidth(self._h, ctypes.byref(gbs)))
+        return float(gbs.value)
 
     def flush_l2(self):
         self._check(self.lib.plb_flush_l2(self._h))

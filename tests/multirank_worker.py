@@ -30,6 +30,10 @@ CASES = {
     "periodic_box": lambda: cases.periodic_box(30, 22),
     "mrt_box": lambda: _mrt(cases.periodic_box(30, 22)),
     "spin": lambda: _centered(cases.cylinder(64, 31, radius=5, spin=0.01)),
+    # slabs of 2 (four ranks) / 4 (two ranks) columns: every column is an edge
+    "thin": lambda: cases.poiseuille(8, 21),
+    # uneven ceil split (parallel/domain.py:54-66): 19 + 18, or 10 + 10 + 10 + 7
+    "uneven": lambda: cases.cavity(37, 29),
 }
 
 

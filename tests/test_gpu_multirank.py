@@ -39,10 +39,13 @@ NAMES = ["cavity", "poiseuille", "cylinder_cut", "periodic_box", "mrt_box",
 TWO_SLABS = ([f"{n}:25:strict:p2p" for n in NAMES] +
              [f"{n}:25:production:nccl" for n in NAMES] +
              ["periodic_box:25:production:p2p", "cylinder_cut:25:strict:nccl",
-              "periodic_box:400:strict:p2p", "poiseuille:400:strict:nccl"])
+              "periodic_box:400:strict:p2p", "poiseuille:400:strict:nccl",
+              "thin:60:strict:p2p", "thin:60:strict:nccl"])
 FOUR_SLABS = ([f"{n}:25:strict:p2p" for n in
                ("poiseuille", "cylinder_cut", "periodic_box")] +
-              ["periodic_box:25:strict:nccl", "mrt_box:300:production:p2p"])
+              ["periodic_box:25:strict:nccl", "mrt_box:300:production:p2p",
+               "thin:60:strict:p2p", "thin:60:strict:nccl",
+               "uneven:40:strict:p2p"])
 
 
 def _launch(world, specs, port):

@@ -135,6 +135,12 @@ ORACLE_ONLY_CASES = {
     "cavity_101": lambda: cases.cavity(101, 101),
     "odd_sizes": lambda: cases.periodic_box(67, 131),
     "wide_row": lambda: cases.poiseuille(9, 300),
+    # degenerate slabs: the periodic seam when the slab is 2 or 3 columns wide
+    # (every column is a slab-edge column), a two-row y-periodic channel
+    # (a one-node-wide grid is rejected like in the reference, base/mesh.py)
+    "two_columns_periodic": lambda: cases.poiseuille(2, 21),
+    "three_columns_periodic": lambda: _mrt(cases.poiseuille(3, 21)),
+    "two_rows_y_periodic": lambda: cases.channel_y(19, 2),
 }
 
 
