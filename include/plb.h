@@ -207,6 +207,10 @@ int plb_profile_read(plb_handle h, double *bulk_ms, int64_t *n_launches);
 int plb_info(plb_handle h, int64_t out[8]);
 /* Kernels launched by this handle since creation / since the last reset. */
 int64_t plb_kernel_launches(plb_handle h, int32_t reset);
+/* PCI bus id ("0000:1b:00.0") of a CUDA device ordinal, so that the host side
+ * can bind the rank to the NUMA node the GPU hangs off before it allocates
+ * its transfer buffers (no handle needed). */
+int plb_device_pci_bus_id(int32_t device, char *buf, int32_t len);
 /* Pinned host memory for upload / download buffers. */
 int plb_host_alloc(void **ptr, size_t bytes);
 int plb_host_free(void *ptr);

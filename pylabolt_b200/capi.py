@@ -31,6 +31,7 @@ EXPORTS = [
     "plb_host_alloc", "plb_host_free", "plb_flush_l2",
     "plb_profile_enable", "plb_profile_read", "plb_info",
     "plb_link_nodes", "plb_download_link_exchange", "plb_copy_bandwidth",
+    "plb_device_pci_bus_id",
 ]
 STORE_MOMENTS, RECORD_LINKS = 1, 2
 # plb_info()["faces"]: how the slab-face populations travel
@@ -107,8 +108,18 @@ def load_library(strict=None):
                                    ctypes.POINTER(i64)]
     lib.plb_download_link_exchange.argtypes = [vp, ctypes.POINTER(dbl), i64]
     lib.plb_copy_bandwidth.argtypes = [vp, ctypes.POINTER(dbl)]
+    lib.plb_device_pci_bus_id.argtypes = [i32, ctypes.c_char_p, i32]
     _libs[strict] = lib
     return lib
+
+
+def device_pci_bus_id(device, strict=None):
+    """'0000:1b:00.0' of a CUDA device ordinal."""
+    lib = load_library(strict)
+    buf = ctypes.create_string_buffer(64)
+    if lib.plb_device_pci_bus_id(int(device), buf, 64) != 0:
+        raise PlbError(lib.plb_last_error().decode())
+    return buf.value.decode().lower()
 
 
 def _i64(values):

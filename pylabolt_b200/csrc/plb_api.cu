@@ -1204,6 +1204,13 @@ int64_t plb_kernel_launches(plb_handle s, int32_t reset)
     return n;
 }
 
+int plb_device_pci_bus_id(int32_t device, char *buf, int32_t len)
+{
+    if (!buf || len < 16) return fail(PLB_ERR_INVALID, "buffer too small");
+    CUDA_TRY(cudaDeviceGetPCIBusId(buf, len, device));
+    return PLB_OK;
+}
+
 int plb_host_alloc(void **ptr, size_t bytes)
 {
     if (!ptr) return fail(PLB_ERR_INVALID, "null argument");

@@ -12,6 +12,7 @@ There is no CPU path: without the CUDA library or a CUDA device the solver
 raises.
 """
 import os
+import sys
 import time
 
 import numpy as np
@@ -48,6 +49,20 @@ class Backend:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.device = device
         capi.load_library(strict)      # fail loudly now, not at the first step
+        # run (and allocate transfer buffers) on the GPU's own CPU socket
+        self.numa_node = None
+        if state.domain.mpi_size > 1:
+            from .affinity import bind_to_gpu
+            try:
+                self.numa_node = bind_to_gpu(
+                    capi.device_pci_bus_id(self.device, strict))
+            except capi.PlbError:
+                pass                   # plb_create reports the missing device
+            if os.environ.get("PLB_DEBUG"):
+                print(f"[plb] rank {rank} device {self.device}: NUMA node "
+                      f"{self.numa_node}, cpus "
+                      f"{len(os.sched_getaffinity(0))}", file=sys.stderr,
+                      flush=True)
         print_log(f"{'Backend':<25}: b200 (sm_100a, libplb)", rank, verbose)
         print_log(f"{'CUDA device':<25}: {self.device}", rank, verbose)
 
