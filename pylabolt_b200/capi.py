@@ -66,9 +66,9 @@ def load_library(strict=None):
     if strict is None:
         strict = os.environ.get("PLB_STRICT", "0") not in ("", "0")
     strict = bool(strict)
-    if strict in _libs:
-        return _libs[strict]
     path = os.environ.get("PLB_LIB") or _build.lib_path(strict)
+    if path in _libs:
+        return _libs[path]
     if not os.path.exists(path):
         raise PlbError(
             f"{path} is missing: the b200 back end has no CPU fallback. "
@@ -109,7 +109,7 @@ def load_library(strict=None):
     lib.plb_download_link_exchange.argtypes = [vp, ctypes.POINTER(dbl), i64]
     lib.plb_copy_bandwidth.argtypes = [vp, ctypes.POINTER(dbl)]
     lib.plb_device_pci_bus_id.argtypes = [i32, ctypes.c_char_p, i32]
-    _libs[strict] = lib
+    _libs[path] = lib
     return lib
 
 

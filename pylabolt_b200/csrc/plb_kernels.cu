@@ -20,6 +20,20 @@
 //                                 three populations that cross a face
 #include "plb_collide.cuh"
 
+// Every kernel launch goes through PLB_LAUNCH.  MODE documents (and, in the
+// host-side SIMT emulation used by tests/emu, selects) how the kernel's
+// threads cooperate: SIMPLE = independent threads, COOP = warp shuffles /
+// votes / __syncthreads.  The kernel name is parenthesised so that template
+// arguments with commas survive the preprocessor.
+#define PLB_UNPAREN(...) __VA_ARGS__
+#ifdef PLB_EMU_RUNTIME
+#define PLB_LAUNCH(MODE, KERNEL, GRID, BLOCK, STREAM, ...)                    \
+    PLB_EMU_LAUNCH(MODE, (PLB_UNPAREN KERNEL), GRID, BLOCK, __VA_ARGS__)
+#else
+#define PLB_LAUNCH(MODE, KERNEL, GRID, BLOCK, STREAM, ...)                    \
+    PLB_UNPAREN KERNEL<<<(GRID), (BLOCK), 0, (STREAM)>>>(__VA_ARGS__)
+#endif
+
 namespace plb {
 
 // ---------------------------------------------------------------------------
@@ -392,10 +406,14 @@ __global__ void k_face_signal(unsigned long long *flag_a,
 __device__ __forceinline__ unsigned long long ld_acquire_sys(
     const unsigned long long *p)
 {
+#ifdef PLB_EMU_RUNTIME
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+#else
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p)
                  : "memory");
     return v;
+#endif
 }
 
 // Delivery of the three populations that crossed a slab face (or the
@@ -596,8 +614,7 @@ struct BulkScalar {
                     cudaStream_t st)
     {
         const int32_t chunks = int32_t((a.p.L.ny + 255) / 256);
-        k_bulk_scalar<C, F, S><<<unsigned(n_rows * chunks), 256, 0, st>>>(
-            a, x_begin, chunks);
+        PLB_LAUNCH(SIMPLE, (k_bulk_scalar<C, F, S>), unsigned(n_rows * chunks), 256, st, a, x_begin, chunks);
     }
 };
 
@@ -608,8 +625,7 @@ struct BulkVec2 {
     {
         constexpr int span = 2 * PLB_BLOCK;
         const int32_t chunks = int32_t((a.p.L.ny + span - 1) / span);
-        k_bulk_vec2<C, F, S><<<unsigned(n_rows * chunks), PLB_BLOCK, 0, st>>>(
-            a, x_begin, chunks);
+        PLB_LAUNCH(COOP, (k_bulk_vec2<C, F, S>), unsigned(n_rows * chunks), PLB_BLOCK, st, a, x_begin, chunks);
     }
 };
 
@@ -619,8 +635,7 @@ struct BulkEdge {
                     cudaStream_t st)
     {
         const int32_t chunks = int32_t((a.p.L.ny + 255) / 256);
-        k_bulk_edge<C, F, S><<<unsigned(n_rows * chunks), 256, 0, st>>>(
-            a, x_begin, chunks);
+        PLB_LAUNCH(SIMPLE, (k_bulk_edge<C, F, S>), unsigned(n_rows * chunks), 256, st, a, x_begin, chunks);
     }
 };
 
@@ -629,8 +644,7 @@ struct Links {
     static void run(const StepArgs &a, const LinkNode *nodes, int64_t n,
                     const ElementDev *el, cudaStream_t st)
     {
-        k_links<C, F, S><<<unsigned((n + 127) / 128), 128, 0, st>>>(a, nodes, n,
-                                                                    el);
+        PLB_LAUNCH(SIMPLE, (k_links<C, F, S>), unsigned((n + 127) / 128), 128, st, a, nodes, n, el);
     }
 };
 
@@ -661,7 +675,7 @@ int launch_bulk_edge(const StepArgs &a, int64_t x_begin, int64_t x_end,
 int launch_face_signal(unsigned long long *flag_a, unsigned long long *flag_b,
                        unsigned long long value, cudaStream_t stream)
 {
-    k_face_signal<<<1, 1, 0, stream>>>(flag_a, flag_b, value);
+    PLB_LAUNCH(SIMPLE, (k_face_signal), 1, 1, stream, flag_a, flag_b, value);
     return 1;
 }
 
@@ -678,8 +692,7 @@ int launch_zero_gradient(double *fout, int64_t plane, const ZgLink *links,
                          int64_t n_links, cudaStream_t stream)
 {
     if (n_links <= 0) return 0;
-    k_zero_gradient<<<unsigned((n_links + 127) / 128), 128, 0, stream>>>(
-        fout, plane, links, n_links);
+    PLB_LAUNCH(SIMPLE, (k_zero_gradient), unsigned((n_links + 127) / 128), 128, stream, fout, plane, links, n_links);
     return 1;
 }
 
@@ -691,10 +704,7 @@ int launch_face_unpack(const Layout &L, double *fout, int64_t x_col,
                        unsigned long long wait_value, unsigned long long *status,
                        long long spin_budget)
 {
-    k_face_unpack<<<unsigned((L.ny + 255) / 256), 256, 0, stream>>>(
-        L, fout, x_col, dirs[0], dirs[1], dirs[2], src, src_stride0,
-        src_stride1, src_stride2, mask, wait_flag, wait_value, status,
-        spin_budget);
+    PLB_LAUNCH(SIMPLE, (k_face_unpack), unsigned((L.ny + 255) / 256), 256, stream, L, fout, x_col, dirs[0], dirs[1], dirs[2], src, src_stride0, src_stride1, src_stride2, mask, wait_flag, wait_value, status, spin_budget);
     return 1;
 }
 
@@ -702,8 +712,7 @@ int launch_init_pop(const KParams &p, double *f, const uint8_t *code,
                     const double *rho, const double *ux, const double *uy,
                     cudaStream_t stream)
 {
-    k_init_pop<<<unsigned((p.L.plane + 255) / 256), 256, 0, stream>>>(
-        p, f, code, rho, ux, uy);
+    PLB_LAUNCH(SIMPLE, (k_init_pop), unsigned((p.L.plane + 255) / 256), 256, stream, p, f, code, rho, ux, uy);
     return 1;
 }
 
@@ -712,8 +721,7 @@ int launch_unpack_rows(const Layout &L, const double *staging, int ncomp,
                        int64_t nrows, cudaStream_t stream)
 {
     const int64_t n = nrows * (L.ny + 2);
-    k_unpack_rows<<<unsigned((n + 255) / 256), 256, 0, stream>>>(
-        L, staging, ncomp, planes, plane_stride, row0, nrows);
+    PLB_LAUNCH(SIMPLE, (k_unpack_rows), unsigned((n + 255) / 256), 256, stream, L, staging, ncomp, planes, plane_stride, row0, nrows);
     return 1;
 }
 
@@ -723,8 +731,7 @@ int launch_pack_rows(const Layout &L, double *staging, int ncomp,
                      cudaStream_t stream)
 {
     const int64_t n = nrows * (L.ny + 2);
-    k_pack_rows<<<unsigned((n + 255) / 256), 256, 0, stream>>>(
-        L, staging, ncomp, planes, plane_stride, row0, nrows, zero_mode);
+    PLB_LAUNCH(SIMPLE, (k_pack_rows), unsigned((n + 255) / 256), 256, stream, L, staging, ncomp, planes, plane_stride, row0, nrows, zero_mode);
     return 1;
 }
 
@@ -733,8 +740,7 @@ int launch_pack_inner(const Layout &L, double *staging, int ncomp,
                       int64_t nrows, cudaStream_t stream)
 {
     const int64_t n = nrows * L.ny;
-    k_pack_inner<<<unsigned((n + 255) / 256), 256, 0, stream>>>(
-        L, staging, ncomp, planes, plane_stride, x0, nrows);
+    PLB_LAUNCH(SIMPLE, (k_pack_inner), unsigned((n + 255) / 256), 256, stream, L, staging, ncomp, planes, plane_stride, x0, nrows);
     return 1;
 }
 
@@ -743,15 +749,14 @@ int launch_residue(const Layout &L, const uint8_t *code, const double *rho,
                    double *ux_old, double *uy_old, double *partials,
                    int n_blocks, double *out6, cudaStream_t stream)
 {
-    k_residue_partial<<<n_blocks, RES_THREADS, 0, stream>>>(
-        L, code, rho, ux, uy, rho_old, ux_old, uy_old, partials);
-    k_residue_final<<<1, 32, 0, stream>>>(partials, n_blocks, out6);
+    PLB_LAUNCH(COOP, (k_residue_partial), n_blocks, RES_THREADS, stream, L, code, rho, ux, uy, rho_old, ux_old, uy_old, partials);
+    PLB_LAUNCH(SIMPLE, (k_residue_final), 1, 32, stream, partials, n_blocks, out6);
     return 2;
 }
 
 int launch_fill(double *buf, int64_t n, double value, cudaStream_t stream)
 {
-    k_fill<<<148 * 8, 256, 0, stream>>>(buf, n, value);
+    PLB_LAUNCH(SIMPLE, (k_fill), 148 * 8, 256, stream, buf, n, value);
     return 1;
 }
 
