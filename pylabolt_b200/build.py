@@ -57,11 +57,18 @@ def _stale(target):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra_flags=()):
+def build(force=False, verbose=False, extra_flags=(), variant=None):
+    """variant: build lib/variants/libplb_<variant>.so (production flags plus
+    extra_flags) instead of the two shipped libraries -- tuning experiments."""
     os.makedirs(LIB_DIR, exist_ok=True)
     built = []
     for strict in (False, True):
         target = lib_path(strict)
+        if variant is not None:
+            if strict:
+                continue
+            os.makedirs(os.path.join(LIB_DIR, "variants"), exist_ok=True)
+            target = os.path.join(LIB_DIR, "variants", f"libplb_{variant}.so")
         if not force and not _stale(target):
             continue
         cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags)

@@ -31,7 +31,7 @@ EXPORTS = [
     "plb_host_alloc", "plb_host_free", "plb_flush_l2",
     "plb_profile_enable", "plb_profile_read", "plb_info",
     "plb_link_nodes", "plb_download_link_exchange", "plb_copy_bandwidth",
-    "plb_device_pci_bus_id",
+    "plb_device_pci_bus_id", "plb_fused_info",
 ]
 STORE_MOMENTS, RECORD_LINKS = 1, 2
 # plb_info()["faces"]: how the slab-face populations travel
@@ -104,6 +104,7 @@ def load_library(strict=None):
     lib.plb_profile_read.argtypes = [vp, ctypes.POINTER(dbl),
                                      ctypes.POINTER(i64)]
     lib.plb_info.argtypes = [vp, ctypes.POINTER(i64)]
+    lib.plb_fused_info.argtypes = [vp, ctypes.POINTER(i64)]
     lib.plb_link_nodes.argtypes = [vp, ctypes.POINTER(i64), i64,
                                    ctypes.POINTER(i64)]
     lib.plb_download_link_exchange.argtypes = [vp, ctypes.POINTER(dbl), i64]
@@ -332,6 +333,14 @@ class Plb:
         self._check(self.lib.plb_info(self._h, out))
         keys = ("n_bulk", "n_link", "n_solid", "pitch", "plane", "variant",
                 "n_bulk_timed", "faces")
+        return dict(zip(keys, out[:8]))
+
+    def fused_info(self):
+        """State of the two-steps-per-pass path (plb_fused_info)."""
+        out = (ctypes.c_int64 * 8)()
+        self._check(self.lib.plb_fused_info(self._h, out))
+        keys = ("active", "n_deep", "n_list1", "n_list2", "pairs", "rows",
+                "strips", "mode")
         return dict(zip(keys, out[:8]))
 
     def copy_bandwidth(self):

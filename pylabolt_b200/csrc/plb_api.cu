@@ -45,6 +45,10 @@ int fail(int code, const char *fmt, ...)
                         cudaGetErrorString(err__), __FILE__, __LINE__);       \
     } while (0)
 
+#ifndef PLB_FUSE_DEFAULT
+#define PLB_FUSE_DEFAULT 1
+#endif
+
 constexpr size_t XBUF_MAILBOX = 256;   // bytes reserved for the p2p mailbox words
 
 constexpr int CX[Q] = PLB_CX_LIST;
@@ -157,6 +161,18 @@ struct plb_solver {
     unsigned char *xbuf = nullptr;
     unsigned char *peer_left = nullptr, *peer_right = nullptr;   // their xbuf
     long long spin_budget = 0;
+
+    // Two steps per pass (step_pair): PLB_FUSE = 0 off, 1 when the geometry
+    // qualifies (default), 2 whenever there is a deep node at all.
+    int fuse_mode = PLB_FUSE_DEFAULT;
+    bool fused_ok = false;
+    double *f_mid = nullptr;             // scratch lattice (lazy)
+    uint8_t *deep_dev = nullptr;         // 1 = bulk node with eight bulk neighbours
+    LinkNode *list1_dev = nullptr, *list2_dev = nullptr;
+    int64_t n_list1 = 0, n_list2 = 0, n_deep = 0;
+    int32_t fused_rows = 64;             // rows a warp marches over (PLB_FUSED_ROWS)
+    int64_t pending = 0;                 // plain steps held back for pairing
+    int64_t pairs_done = 0;
 
     int64_t launches = 0;
     int64_t steps_done = 0;
@@ -379,44 +395,39 @@ int bulk_timed(plb_solver *s, const StepArgs &a, int64_t x0, int64_t x1,
     return PLB_OK;
 }
 
-int step_once(plb_solver *s, bool store, bool record)
+StepArgs step_args(const plb_solver *s, const double *fin, double *fout)
 {
-    const Layout &L = s->L;
     StepArgs a;
     a.p = s->kp;
-    a.fin = s->f[s->cur];
-    a.fout = s->f[s->cur ^ 1];
+    a.fin = fin;
+    a.fout = fout;
     a.code = s->code;
     a.rho = s->rho();
     a.ux = s->ux();
     a.uy = s->uy();
     a.collision = s->kernel_collision;
     a.forcing = s->cfg.forcing;
-    a.store = store ? 1 : 0;
+    a.store = 0;
     a.exch = nullptr;
-    if (record && s->n_links > 0) {
-        if (!s->exch_dev)
-            CUDA_TRY(cudaMalloc(&s->exch_dev, size_t(s->n_links) * 8 * sizeof(double)));
-        a.exch = s->exch_dev;
-    }
+    return a;
+}
+
+// The O(perimeter) part of step number t, all on the edge stream: with slab
+// faces the two edge columns first (they feed the faces; `edge_columns`), then
+// the listed nodes, then the face exchange (peer-to-peer stores or NCCL
+// between ranks, this rank's own ghost rows for a single-rank periodic seam)
+// and its delivery into a.fout.  Returns in [x_lo, x_hi) the columns that are
+// left for the bulk kernel.
+int edge_chain(plb_solver *s, StepArgs a, unsigned long long t, const LinkNode *list,
+               int64_t n_list, bool edge_columns, int64_t *x_lo, int64_t *x_hi)
+{
+    const Layout &L = s->L;
+    cudaStream_t es = s->edge_stream;
     double *fout = a.fout;
     const int32_t right_dirs[3] = {1, 5, 8}, left_dirs[3] = {3, 6, 7};
     const bool faces = s->cfg.left_neighbor || s->cfg.right_neighbor;
-
-    // Two concurrent chains that write disjoint slots of lattice B.
-    //   edge stream (high priority): the O(perimeter) work -- with slab faces
-    //     the two edge columns first (they feed the faces), then the link
-    //     nodes, the face exchange (NCCL between ranks, this rank's own ghost
-    //     rows for a single-rank periodic seam) and its delivery;
-    //   main stream: the bulk kernel on all other columns.
-    // They join before the zero_gradient pass, so the small kernels and the
-    // exchange latency hide behind the bulk pass.
-    cudaStream_t es = s->edge_stream;
-    CUDA_TRY(cudaEventRecord(s->ev_edge, s->stream));
-    CUDA_TRY(cudaStreamWaitEvent(es, s->ev_edge, 0));
     // peer-to-peer faces: this step's parity selects the half of the
     // neighbours' receive buffers that the edge kernels store into
-    const unsigned long long t = (unsigned long long)(s->steps_done + 1);
     const int64_t half = 3 * L.pitch;                 // doubles per parity
     const int64_t par_off = int64_t(t & 1) * half;
     if (s->p2p) {
@@ -428,17 +439,18 @@ int step_once(plb_solver *s, bool store, bool record)
             a.face_hi = reinterpret_cast<double *>(s->peer_right + XBUF_MAILBOX) +
                         par_off;
     }
-    int64_t x_lo = 0, x_hi = L.nx;
-    if (faces && L.nx > 2) {
+    *x_lo = 0;
+    *x_hi = L.nx;
+    if (edge_columns && faces && L.nx > 2) {
         if (int rc = bulk_timed(s, a, 0, 1, es, false, s->p2p)) return rc;
         if (int rc = bulk_timed(s, a, L.nx - 1, L.nx, es, false, s->p2p)) return rc;
-        x_lo = 1;
-        x_hi = L.nx - 1;
-    } else if (faces) {
+        *x_lo = 1;
+        *x_hi = L.nx - 1;
+    } else if (edge_columns && faces) {
         if (int rc = bulk_timed(s, a, 0, L.nx, es, true, s->p2p)) return rc;
-        x_lo = x_hi = 0;
+        *x_lo = *x_hi = 0;
     }
-    s->launches += launch_links(a, s->links_dev, s->n_links, s->elements_dev, es);
+    s->launches += launch_links(a, list, n_list, s->elements_dev, es);
     if (!s->comm) {
         // single rank: the periodic image is this rank's own ghost column
         if (s->cfg.left_neighbor)
@@ -500,14 +512,143 @@ int step_once(plb_solver *s, bool store, bool record)
                                               s->recv_right, 0, L.ny, 2 * L.ny,
                                               s->mask_right, es);
     }
+    return PLB_OK;
+}
+
+int step_once(plb_solver *s, bool store, bool record)
+{
+    StepArgs a = step_args(s, s->f[s->cur], s->f[s->cur ^ 1]);
+    a.store = store ? 1 : 0;
+    if (record && s->n_links > 0) {
+        if (!s->exch_dev)
+            CUDA_TRY(cudaMalloc(&s->exch_dev, size_t(s->n_links) * 8 * sizeof(double)));
+        a.exch = s->exch_dev;
+    }
+
+    // Two concurrent chains that write disjoint slots of lattice B.
+    //   edge stream (high priority): the O(perimeter) work (edge_chain);
+    //   main stream: the bulk kernel on all other columns.
+    // They join before the zero_gradient pass, so the small kernels and the
+    // exchange latency hide behind the bulk pass.
+    cudaStream_t es = s->edge_stream;
+    CUDA_TRY(cudaEventRecord(s->ev_edge, s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(es, s->ev_edge, 0));
+    const unsigned long long t = (unsigned long long)(s->steps_done + 1);
+    int64_t x_lo = 0, x_hi = 0;
+    if (int rc = edge_chain(s, a, t, s->links_dev, s->n_links, true, &x_lo, &x_hi))
+        return rc;
     CUDA_TRY(cudaEventRecord(s->ev_comm, es));
-    a.face_lo = a.face_hi = nullptr;
     if (int rc = bulk_timed(s, a, x_lo, x_hi, s->stream, true)) return rc;
     CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
-    run_zero_gradient(s, fout, s->stream);
+    run_zero_gradient(s, a.fout, s->stream);
     s->cur ^= 1;
     s->steps_done += 1;
     return PLB_OK;
+}
+
+// Two steps as one pass (k_bulk_fused2 in plb_kernels.cu).  A = time t,
+// B = time t + 2, M = a scratch lattice that holds time t + 1 on the nodes
+// that are NOT deep:
+//   edge stream: step t+1 on list 1 (the non-deep fluid nodes and the deep
+//                nodes next to them) A -> M, faces, zero_gradient on M;
+//                step t+2 on list 2 (the non-deep fluid nodes) M -> B, faces;
+//   main stream: both steps of every deep node, A -> B;
+//   join, zero_gradient on B.
+// Slot (n, k) of B has one writer: the owner n - c_k (deep: the fused kernel,
+// else the second list pass), n itself (bounce back / element / uncovered
+// ghost), or the face delivery.  Every slot of M that the second list pass
+// reads (all nine of every non-deep fluid node) is written by the first one:
+// its source is a non-deep node, a deep node next to a non-deep one (both on
+// list 1), the node itself, or the face delivery.  The per-step protocol
+// between ranks (stores, mailbox value t, delivery) is the one of step_once,
+// so a neighbour may run the same two steps unfused.
+int step_pair(plb_solver *s)
+{
+    const Layout &L = s->L;
+    if (!s->f_mid) {
+        const size_t bytes = size_t(Q) * L.plane * sizeof(double);
+        if (cudaMalloc(&s->f_mid, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            s->f_mid = nullptr;
+            s->fused_ok = false;       // no room for the scratch lattice
+            return PLB_ERR_NOMEM;
+        }
+        CUDA_TRY(cudaMemsetAsync(s->f_mid, 0, bytes, s->stream));
+    }
+    double *A = s->f[s->cur], *B = s->f[s->cur ^ 1], *M = s->f_mid;
+    cudaStream_t es = s->edge_stream;
+    CUDA_TRY(cudaEventRecord(s->ev_edge, s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(es, s->ev_edge, 0));
+    const unsigned long long t1 = (unsigned long long)(s->steps_done + 1);
+    int64_t x_lo = 0, x_hi = 0;
+    if (int rc = edge_chain(s, step_args(s, A, M), t1, s->list1_dev, s->n_list1, false,
+                            &x_lo, &x_hi))
+        return rc;
+    run_zero_gradient(s, M, es);
+    if (int rc = edge_chain(s, step_args(s, M, B), t1 + 1, s->list2_dev, s->n_list2,
+                            false, &x_lo, &x_hi))
+        return rc;
+    CUDA_TRY(cudaEventRecord(s->ev_comm, es));
+
+    const StepArgs a = step_args(s, A, B);
+    const bool prof = s->profile;
+    if (prof) {
+        if (s->prof_used + 2 > s->prof_events.size())
+            for (int i = 0; i < 2; ++i) {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreate(&e));
+                s->prof_events.push_back(e);
+            }
+        CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used], s->stream));
+    }
+    s->launches += launch_bulk_fused(a, s->deep_dev, 0, L.nx, s->fused_rows, s->stream);
+    if (prof) {
+        CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used + 1], s->stream));
+        s->prof_used += 2;
+    }
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
+    run_zero_gradient(s, B, s->stream);
+    s->cur ^= 1;
+    s->steps_done += 2;
+    s->pairs_done += 1;
+    return PLB_OK;
+}
+
+bool fused_active(const plb_solver *s)
+{
+    return s->fused_ok && s->fuse_mode != 0;
+}
+
+// n steps; `flags` apply to the last one.  Steps that need neither moments nor
+// the link record go two at a time when the fused path is active.
+int run_steps(plb_solver *s, int64_t n, int32_t flags)
+{
+    int64_t i = 0;
+    const int64_t plain = flags ? n - 1 : n;
+    while (fused_active(s) && plain - i >= 2) {
+        const int rc = step_pair(s);
+        if (rc == PLB_ERR_NOMEM && !s->fused_ok) break;   // fall through unfused
+        if (rc) return rc;
+        i += 2;
+    }
+    for (; i < n; ++i) {
+        const bool last = i == n - 1;
+        if (int rc = step_once(s, last && (flags & PLB_STORE_MOMENTS),
+                               last && (flags & PLB_RECORD_LINKS)))
+            return rc;
+    }
+    return PLB_OK;
+}
+
+// plb_step() is asynchronous; with the fused path a single plain step is held
+// back until its partner arrives (or until any other entry point needs the
+// state), so that a host loop that issues one step per call -- the
+// reference's Solver.run -- still advances two steps per pass.
+int flush_pending(plb_solver *s)
+{
+    const int64_t n = s->pending;
+    s->pending = 0;
+    return n > 0 ? run_steps(s, n, 0) : PLB_OK;
 }
 
 // Peer-to-peer slab faces.  Every rank exports one exchange buffer with CUDA
@@ -670,6 +811,8 @@ int plb_create(const plb_config *c, plb_handle *out)
     }
     if (const char *v = getenv("PLB_KERNEL"))
         s->variant = (strcmp(v, "scalar") == 0) ? 0 : 1;
+    if (const char *v = getenv("PLB_FUSE")) s->fuse_mode = atoi(v);
+    if (s->fuse_mode < 0 || s->fuse_mode > 2) s->fuse_mode = PLB_FUSE_DEFAULT;
     s->kernel_collision = c->collision;
     if (c->collision == PLB_MRT) {
         // S = (1,..,1,s7,s8) as in base/collision_operator.py:159-163 needs
@@ -728,6 +871,10 @@ void plb_destroy(plb_handle s)
     close_p2p(s);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (int i = 0; i < 2; ++i) cudaFree(s->f[i]);
+    cudaFree(s->f_mid);
+    cudaFree(s->deep_dev);
+    cudaFree(s->list1_dev);
+    cudaFree(s->list2_dev);
     cudaFree(s->mom);
     cudaFree(s->mom_old);
     cudaFree(s->res_partials);
@@ -885,6 +1032,70 @@ int plb_finalize_geometry(plb_handle s)
         }
     }
 
+    // Two-steps-per-pass mode: DEEP nodes (bulk, all eight neighbours bulk) are
+    // advanced by k_bulk_fused2; list 2 holds every other fluid node, list 1
+    // additionally the deep nodes that push into one of those (step_pair).
+    {
+        std::vector<uint8_t> deep(size_t(L.plane), 0);
+        const int64_t P = L.pitch;
+        int64_t n_deep = 0;
+        for (int64_t x = 1; x + 1 < nx; ++x) {
+            const uint8_t *c = code.data() + L.at(x, 0);
+            uint8_t *d = deep.data() + L.at(x, 0);
+            for (int64_t y = 1; y + 1 < ny; ++y) {
+                const uint8_t any = c[y] | c[y - 1] | c[y + 1] | c[y - P] | c[y - P - 1] |
+                                    c[y - P + 1] | c[y + P] | c[y + P - 1] | c[y + P + 1];
+                d[y] = any == NODE_BULK;
+                n_deep += d[y];
+            }
+        }
+        std::vector<LinkNode> list1, list2;
+        size_t next_link = 0;
+        for (int64_t x = 0; x < nx; ++x) {
+            const uint8_t *c = code.data() + L.at(x, 0);
+            const uint8_t *d = deep.data() + L.at(x, 0);
+            for (int64_t y = 0; y < ny; ++y) {
+                if (c[y] == NODE_LINK) {
+                    const LinkNode &ln = link_nodes[next_link++];   // same (x, y) order
+                    list1.push_back(ln);
+                    list2.push_back(ln);
+                } else if (c[y] == NODE_BULK && !d[y]) {
+                    list1.push_back(LinkNode{int32_t(x), int32_t(y), 0});
+                    list2.push_back(LinkNode{int32_t(x), int32_t(y), 0});
+                } else if (c[y] == NODE_BULK) {
+                    // deep: all eight neighbours are bulk; on list 1 if one is not deep
+                    const bool ring = !(d[y - 1] & d[y + 1] & d[y - P] & d[y - P - 1] &
+                                        d[y - P + 1] & d[y + P] & d[y + P - 1] &
+                                        d[y + P + 1]);
+                    if (ring) list1.push_back(LinkNode{int32_t(x), int32_t(y), 0});
+                }
+            }
+        }
+        s->n_deep = n_deep;
+        s->n_list1 = int64_t(list1.size());
+        s->n_list2 = int64_t(list2.size());
+        const int64_t n_fluid = n_bulk + int64_t(link_nodes.size());
+        s->fused_ok = n_deep > 0 &&
+                      (s->fuse_mode == 2 || (s->n_list1 * 8 <= n_fluid && n_fluid >= 4096));
+        if (s->fused_ok && s->fuse_mode != 0) {
+            CUDA_TRY(cudaMalloc(&s->deep_dev, deep.size()));
+            CUDA_TRY(cudaMemcpy(s->deep_dev, deep.data(), deep.size(), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMalloc(&s->list1_dev, std::max<size_t>(1, list1.size()) * sizeof(LinkNode)));
+            CUDA_TRY(cudaMemcpy(s->list1_dev, list1.data(), list1.size() * sizeof(LinkNode),
+                                cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMalloc(&s->list2_dev, std::max<size_t>(1, list2.size()) * sizeof(LinkNode)));
+            CUDA_TRY(cudaMemcpy(s->list2_dev, list2.data(), list2.size() * sizeof(LinkNode),
+                                cudaMemcpyHostToDevice));
+            if (const char *v = getenv("PLB_FUSED_ROWS")) {
+                s->fused_rows = std::max(1, atoi(v));
+            } else {
+                // enough warps for ~6 waves of 148 SMs x 16 resident warps
+                const int64_t want = nx * fused_strips(L) / (148 * 16 * 6);
+                s->fused_rows = int32_t(std::min<int64_t>(128, std::max<int64_t>(16, want)));
+            }
+        }
+    }
+
     // device copies
     CUDA_TRY(cudaMemcpy(s->code, code.data(), code.size(), cudaMemcpyHostToDevice));
     s->n_links = int64_t(link_nodes.size());
@@ -938,6 +1149,7 @@ int plb_upload(plb_handle s, int32_t field, const void *host, size_t bytes)
 {
     if (!s || !host) return fail(PLB_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (int rc = flush_pending(s)) return rc;
     const Layout &L = s->L;
     const size_t size = size_t((L.nx + 2) * (L.ny + 2));
     switch (field) {
@@ -964,6 +1176,7 @@ int plb_download(plb_handle s, int32_t field, void *host, size_t bytes)
 {
     if (!s || !host) return fail(PLB_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (int rc = flush_pending(s)) return rc;
     const Layout &L = s->L;
     const size_t size = size_t((L.nx + 2) * (L.ny + 2));
     const size_t inner = size_t(L.nx * L.ny);
@@ -998,6 +1211,7 @@ int plb_initialize_pop(plb_handle s)
     if (!s) return fail(PLB_ERR_INVALID, "null handle");
     if (!s->finalized) return fail(PLB_ERR_STATE, "plb_finalize_geometry not called");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (int rc = flush_pending(s)) return rc;
     s->launches += launch_init_pop(s->kp, s->f[s->cur], s->code, s->rho(), s->ux(),
                                    s->uy(), s->stream);
     CUDA_TRY(cudaMemsetAsync(s->f[s->cur ^ 1], 0, size_t(Q) * s->L.plane * sizeof(double),
@@ -1012,13 +1226,30 @@ int plb_step(plb_handle s, int64_t n_steps, int32_t flags)
     if (!s->finalized) return fail(PLB_ERR_STATE, "plb_finalize_geometry not called");
     if (n_steps < 0) return fail(PLB_ERR_INVALID, "n_steps < 0");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
-    for (int64_t i = 0; i < n_steps; ++i) {
-        const bool last = i == n_steps - 1;
-        if (int rc = step_once(s, last && (flags & PLB_STORE_MOMENTS),
-                               last && (flags & PLB_RECORD_LINKS)))
-            return rc;
+    flags &= PLB_STORE_MOMENTS | PLB_RECORD_LINKS;
+    int64_t n = s->pending + n_steps;
+    s->pending = 0;
+    if (fused_active(s) && flags == 0 && (n & 1)) {
+        // an odd plain step waits for its partner (flush_pending)
+        s->pending = 1;
+        n -= 1;
     }
+    if (int rc = run_steps(s, n, flags)) return rc;
     CUDA_TRY(cudaGetLastError());
+    return PLB_OK;
+}
+
+int plb_fused_info(plb_handle s, int64_t out[8])
+{
+    if (!s || !out) return fail(PLB_ERR_INVALID, "null argument");
+    out[0] = fused_active(s) ? 1 : 0;
+    out[1] = s->n_deep;
+    out[2] = s->n_list1;
+    out[3] = s->n_list2;
+    out[4] = s->pairs_done;
+    out[5] = s->fused_rows;
+    out[6] = fused_strips(s->L);
+    out[7] = s->fuse_mode;
     return PLB_OK;
 }
 
@@ -1045,6 +1276,7 @@ int plb_download_link_exchange(plb_handle s, double *out, int64_t n_values)
     if (!s->exch_dev)
         return fail(PLB_ERR_STATE, "no step was run with PLB_RECORD_LINKS");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (int rc = flush_pending(s)) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, s->exch_dev, size_t(n_values) * sizeof(double),
                              cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1055,6 +1287,7 @@ int plb_sync(plb_handle s)
 {
     if (!s) return fail(PLB_ERR_INVALID, "null handle");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (int rc = flush_pending(s)) return rc;
     CUDA_TRY(cudaStreamSynchronize(s->edge_stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->p2p) {
@@ -1073,6 +1306,7 @@ int plb_residue_sums(plb_handle s, double out[6])
     if (!s || !out) return fail(PLB_ERR_INVALID, "null argument");
     if (!s->finalized) return fail(PLB_ERR_STATE, "plb_finalize_geometry not called");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (int rc = flush_pending(s)) return rc;
     const int n_blocks = 148 * 4;
     const size_t plane_bytes = size_t(s->L.plane) * sizeof(double);
     if (!s->mom_old) {
@@ -1138,6 +1372,7 @@ int plb_event_record(plb_handle s, int32_t slot)
 {
     if (!s || slot < 0 || slot >= 8) return fail(PLB_ERR_INVALID, "bad event slot");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (int rc = flush_pending(s)) return rc;
     CUDA_TRY(cudaEventRecord(s->events[slot], s->stream));
     return PLB_OK;
 }
@@ -1164,6 +1399,7 @@ int plb_profile_read(plb_handle s, double *bulk_ms, int64_t *n_launches)
 {
     if (!s || !bulk_ms || !n_launches) return fail(PLB_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (int rc = flush_pending(s)) return rc;
     double total = 0.0;
     for (size_t i = 0; i + 1 < s->prof_used; i += 2) {
         float ms = 0.f;
@@ -1199,6 +1435,8 @@ int plb_info(plb_handle s, int64_t out[8])
 int64_t plb_kernel_launches(plb_handle s, int32_t reset)
 {
     if (!s) return 0;
+    cudaSetDevice(s->cfg.device);
+    flush_pending(s);
     const int64_t n = s->launches;
     if (reset) s->launches = 0;
     return n;
@@ -1228,6 +1466,7 @@ int plb_flush_l2(plb_handle s)
 {
     if (!s) return fail(PLB_ERR_INVALID, "null handle");
     CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (int rc = flush_pending(s)) return rc;
     const int64_t n = (int64_t(256) << 20) / 8;   // 256 MiB > 126 MB L2
     if (!s->flush_buf) CUDA_TRY(cudaMalloc(&s->flush_buf, size_t(n) * 8));
     s->launches += launch_fill(s->flush_buf, n, 0.0, s->stream);

@@ -111,6 +111,11 @@ struct StepArgs {
 // All return the number of kernels launched (0 if nothing to do).
 int launch_bulk(const StepArgs &a, int64_t x_begin, int64_t x_end, int variant,
                 cudaStream_t stream);
+// Two steps in one pass over the DEEP nodes of columns [x_begin, x_end)
+// (fin = time t, fout = time t + 2); `deep` is one byte per node.
+int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
+                      int64_t x_end, int32_t rows_per_chunk, cudaStream_t stream);
+int fused_strips(const Layout &L);
 // One slab-edge column with the face redirection of StepArgs::face_lo/hi.
 int launch_bulk_edge(const StepArgs &a, int64_t x_begin, int64_t x_end,
                      cudaStream_t stream);

@@ -275,6 +275,187 @@ k_bulk_vec2(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
 }
 
 // ---------------------------------------------------------------------------
+// two time steps in one pass (temporal blocking in registers)
+// ---------------------------------------------------------------------------
+// The single-step kernels above move 144 B per node and step and run at the
+// HBM roofline; the only way past it is to touch HBM less.  k_bulk_fused2
+// advances DEEP nodes (bulk nodes whose eight neighbours are bulk nodes too,
+// `deep` plane) by TWO steps per pass: lattice A (time t) is read once,
+// lattice B (time t + 2) is written once, 72 B per node and step.  The
+// intermediate lattice (time t + 1) never exists in memory:
+//
+//   * a warp owns a strip of 64 consecutive y (two per lane, 128-bit loads) and
+//     marches along x; row r is loaded and collided once ("stage 1"), and its
+//     post-collision populations are kept in registers, already shifted in y
+//     (one shuffle per population with c_y != 0) to the lane that PULLS them;
+//   * the time-(t+1) state of row x is then complete in registers: k = 1, 5, 8
+//     came from row x - 1 (two iterations old), k = 0, 2, 4 from row x (one
+//     iteration old), k = 3, 6, 7 from row x + 1 (fresh).  It is collided again
+//     ("stage 2") and pushed into B exactly like k_bulk_vec2 pushes;
+//   * the two outer nodes of the strip have no y-neighbour inside the warp, so
+//     a warp delivers FUSED_SPAN = 62 of its 64 nodes and strips overlap by two
+//     (3 % redundant stage-1 work, the overlapped loads hit L2); chunks of
+//     rows overlap by two rows in x.  No shared memory, no block barrier.
+//
+// Every node that is not deep (domain edges, obstacle surfaces, slab-edge
+// columns, and the ring around them) is advanced by two ordinary list passes
+// on the edge stream (step_pair in plb_api.cu).  The arithmetic per node and
+// step is the same collide<>() as everywhere else, so the strict build stays
+// bit-identical to the reference.
+constexpr int FUSED_SPAN = 62;
+#ifndef PLB_FUSED_BLOCK
+#define PLB_FUSED_BLOCK 128
+#endif
+#ifndef PLB_FUSED_MINBLOCKS
+#define PLB_FUSED_MINBLOCKS 4
+#endif
+// rows ahead that are prefetched into L2 (0: off)
+#ifndef PLB_FUSED_L2_AHEAD
+#define PLB_FUSED_L2_AHEAD 0
+#endif
+
+// Stage 1 of one row: load the pair (y, y + 1), collide, and hand every
+// post-collision population to the lane that pulls it in the next step:
+// sa[k] is what node y receives in slot k, sb[k] what node y + 1 receives.
+// (For c_y = +1 lane 0's sa and for c_y = -1 lane 31's sb come from outside
+// the warp and are meaningless: those two nodes are not delivered.)
+template <int COLL, int FORCING>
+__device__ __forceinline__ void fused_stage1(const StepArgs &a, int64_t idx,
+                                             bool in_row, double sa[Q],
+                                             double sb[Q])
+{
+    const int64_t plane = a.p.L.plane;
+    double fa[Q], fb[Q], ga[Q], gb[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+        double2 v = make_double2(0.0, 0.0);
+        if (in_row) v = ld2(a.fin + k * plane + idx);
+        fa[k] = v.x;
+        fb[k] = v.y;
+    }
+    collide<COLL, FORCING>(a.p, fa, ga);
+    collide<COLL, FORCING>(a.p, fb, gb);
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+        if (d_cy[k] == 0) {
+            sa[k] = ga[k];
+            sb[k] = gb[k];
+        } else if (d_cy[k] == 1) {          // pulled from y - 1
+            sa[k] = __shfl_up_sync(0xffffffffu, gb[k], 1);
+            sb[k] = ga[k];
+        } else {                            // pulled from y + 1
+            sa[k] = gb[k];
+            sb[k] = __shfl_down_sync(0xffffffffu, ga[k], 1);
+        }
+    }
+}
+
+template <int COLL, int FORCING>
+__global__ void __launch_bounds__(PLB_FUSED_BLOCK, PLB_FUSED_MINBLOCKS)
+k_bulk_fused2(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
+              int64_t x_end, int32_t strips, int32_t rows_per_chunk)
+{
+    const Layout &L = a.p.L;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t chunk = warp / strips;
+    const int32_t strip = int32_t(warp - chunk * strips);
+    const int64_t xs = x_begin + chunk * rows_per_chunk;
+    if (xs >= x_end) return;                       // whole warp
+    const int64_t xe = (xs + rows_per_chunk < x_end) ? xs + rows_per_chunk : x_end;
+    const int64_t y = int64_t(strip) * FUSED_SPAN - 2 + 2 * lane;
+    // the pair lies inside the padded row (y >= -2 is column >= 14)
+    const bool in_row = L.y0 + y + 1 < L.pitch;
+    const int64_t plane = L.plane, pitch = L.pitch;
+
+    // post-collision populations of earlier rows, shifted to their pullers
+    double pa[3], pb[3];   // row x - 1: k = 1, 5, 8
+    double na[3], nb[3];   // row x    : k = 1, 5, 8
+    double ca[3], cb[3];   // row x    : k = 0, 2, 4
+    {
+        double sa[Q], sb[Q];
+        fused_stage1<COLL, FORCING>(a, L.at(xs - 1, y), in_row, sa, sb);
+        pa[0] = sa[1]; pa[1] = sa[5]; pa[2] = sa[8];
+        pb[0] = sb[1]; pb[1] = sb[5]; pb[2] = sb[8];
+        fused_stage1<COLL, FORCING>(a, L.at(xs, y), in_row, sa, sb);
+        na[0] = sa[1]; na[1] = sa[5]; na[2] = sa[8];
+        nb[0] = sb[1]; nb[1] = sb[5]; nb[2] = sb[8];
+        ca[0] = sa[0]; ca[1] = sa[2]; ca[2] = sa[4];
+        cb[0] = sb[0]; cb[1] = sb[2]; cb[2] = sb[4];
+    }
+
+    for (int64_t x = xs; x < xe; ++x) {
+        const int64_t idx = L.at(x, y);
+#if PLB_FUSED_L2_AHEAD > 0 && !defined(PLB_EMU_RUNTIME)
+        if (in_row && ((lane & 7) == 0 || lane == 31) &&
+            x + 1 + PLB_FUSED_L2_AHEAD <= L.nx) {
+            const double *pf = a.fin + idx + (1 + PLB_FUSED_L2_AHEAD) * pitch;
+#pragma unroll
+            for (int k = 0; k < Q; ++k)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + k * plane));
+        }
+#endif
+        uint16_t dd = 0;
+        if (in_row) dd = *reinterpret_cast<const uint16_t *>(deep + idx);
+        // a lane delivers node y unless it is lane 0, node y + 1 unless lane 31
+        const bool da = (dd & 0xff) != 0 && lane != 0;
+        const bool db = (dd >> 8) != 0 && lane != 31;
+
+        double sa[Q], sb[Q];
+        fused_stage1<COLL, FORCING>(a, idx + pitch, in_row, sa, sb);
+
+        // time t + 1 populations of row x
+        double fa[Q], fb[Q], ha[Q], hb[Q];
+        fa[0] = ca[0]; fa[1] = pa[0]; fa[2] = ca[1]; fa[3] = sa[3]; fa[4] = ca[2];
+        fa[5] = pa[1]; fa[6] = sa[6]; fa[7] = sa[7]; fa[8] = pa[2];
+        fb[0] = cb[0]; fb[1] = pb[0]; fb[2] = cb[1]; fb[3] = sb[3]; fb[4] = cb[2];
+        fb[5] = pb[1]; fb[6] = sb[6]; fb[7] = sb[7]; fb[8] = pb[2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            pa[j] = na[j];
+            pb[j] = nb[j];
+        }
+        na[0] = sa[1]; na[1] = sa[5]; na[2] = sa[8];
+        nb[0] = sb[1]; nb[1] = sb[5]; nb[2] = sb[8];
+        ca[0] = sa[0]; ca[1] = sa[2]; ca[2] = sa[4];
+        cb[0] = sb[0]; cb[1] = sb[2]; cb[2] = sb[4];
+
+        if (!__any_sync(0xffffffffu, da || db)) continue;
+        collide<COLL, FORCING>(a.p, fa, ha);
+        collide<COLL, FORCING>(a.p, fb, hb);
+
+        if (__all_sync(0xffffffffu, (da || lane == 0) && (db || lane == 31))) {
+            // all 62 nodes are deep: 128-bit stores, pairs re-aligned by shuffle
+#pragma unroll
+            for (int k = 0; k < Q; ++k) {
+                double *dst = a.fout + k * plane + idx + d_cx[k] * pitch;
+                if (d_cy[k] == 0) {
+                    if (lane == 0) st1(dst + 1, hb[k]);
+                    else if (lane == 31) st1(dst, ha[k]);
+                    else st2(dst, ha[k], hb[k]);
+                } else if (d_cy[k] == 1) {
+                    // values move to y + 1, y + 2: pair [y, y+1] = (left b, own a)
+                    const double up = __shfl_up_sync(0xffffffffu, hb[k], 1);
+                    if (lane != 0) st2(dst, up, ha[k]);
+                } else {
+                    // values move to y - 1, y: pair [y, y+1] = (own b, right a)
+                    const double dn = __shfl_down_sync(0xffffffffu, ha[k], 1);
+                    if (lane != 31) st2(dst, hb[k], dn);
+                }
+            }
+        } else {
+            // strip touches a non-deep node (domain edge, obstacle, its ring)
+#pragma unroll
+            for (int k = 0; k < Q; ++k) {
+                double *dst = a.fout + k * plane + idx + d_cx[k] * pitch + d_cy[k];
+                if (da) st1(dst, ha[k]);
+                if (db) st1(dst + 1, hb[k]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // link nodes
 // ---------------------------------------------------------------------------
 // velocity[ind] as the reference's fixed_pressure kernel would read it
@@ -660,6 +841,40 @@ int launch_bulk(const StepArgs &a, int64_t x_begin, int64_t x_end, int variant,
         dispatch<BulkVec2>(a.collision, a.forcing, a.store != 0, a, x_begin,
                            n_rows, stream);
     return 1;
+}
+
+int fused_strips(const Layout &L)
+{
+    return int((L.ny + 1 + FUSED_SPAN - 1) / FUSED_SPAN);
+}
+
+template <int C, int F>
+static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
+                      int64_t x_end, int32_t rows_per_chunk, cudaStream_t st)
+{
+    const int32_t strips = fused_strips(a.p.L);
+    const int64_t chunks = (x_end - x_begin + rows_per_chunk - 1) / rows_per_chunk;
+    const int64_t warps = chunks * strips;
+    constexpr int wpb = PLB_FUSED_BLOCK / 32;
+    PLB_LAUNCH(COOP, (k_bulk_fused2<C, F>), unsigned((warps + wpb - 1) / wpb),
+               PLB_FUSED_BLOCK, st, a, deep, x_begin, x_end, strips,
+               rows_per_chunk);
+}
+
+int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
+                      int64_t x_end, int32_t rows_per_chunk, cudaStream_t stream)
+{
+    if (x_end <= x_begin) return 0;
+#define PLB_CASE(C, F)                                                        \
+    if (a.collision == C && a.forcing == F) {                                 \
+        run_fused<C, F>(a, deep, x_begin, x_end, rows_per_chunk, stream);     \
+        return 1;                                                             \
+    }
+    PLB_CASE(0, 0) PLB_CASE(0, 1) PLB_CASE(0, 2)
+    PLB_CASE(1, 0) PLB_CASE(1, 1) PLB_CASE(1, 2)
+    PLB_CASE(2, 0) PLB_CASE(2, 1) PLB_CASE(2, 2)
+#undef PLB_CASE
+    return 0;
 }
 
 int launch_bulk_edge(const StepArgs &a, int64_t x_begin, int64_t x_end,

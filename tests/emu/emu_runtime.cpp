@@ -182,29 +182,25 @@ uint64_t warp_exchange(uint64_t mine, int src)
     return r;
 }
 
-unsigned warp_active_mask()
-{
-    const int w = g_cur / 32;
-    unsigned m = 0;
-    for (int l = 0; l < 32; ++l) {
-        const int t = w * 32 + l;
-        if (t < g_n && !g_fiber[t].done) m |= 1u << l;
-    }
-    return m;
-}
-
-unsigned warp_ballot(bool pred)
+// Votes and the mask of participating lanes are taken between the same two
+// barriers: a lane that leaves the kernel right after the vote must not change
+// what a slower lane sees.
+unsigned warp_ballot(bool pred, unsigned *active)
 {
     need_coop("warp vote in a kernel launched in SIMPLE mode");
     const int w = g_cur / 32;
     g_pred[g_cur] = pred;
     wait(g_warp_barrier[w], g_alive_warp[w]);
-    unsigned m = 0;
+    unsigned m = 0, act = 0;
     for (int l = 0; l < 32; ++l) {
         const int t = w * 32 + l;
-        if (t < g_n && !g_fiber[t].done && g_pred[t]) m |= 1u << l;
+        if (t < g_n && !g_fiber[t].done) {
+            act |= 1u << l;
+            if (g_pred[t]) m |= 1u << l;
+        }
     }
     wait(g_warp_barrier[w], g_alive_warp[w]);
+    if (active) *active = act;
     return m;
 }
 

@@ -25,8 +25,7 @@ void sync_warp();
 // published by lane `src` (or the caller's own when src is out of range or
 // that lane has exited)
 uint64_t warp_exchange(uint64_t mine, int src);
-unsigned warp_ballot(bool pred);
-unsigned warp_active_mask();
+unsigned warp_ballot(bool pred, unsigned *active = nullptr);
 long long clock_ticks();
 
 template <typename T>
@@ -83,7 +82,9 @@ static inline T __shfl_sync(unsigned, T v, int src)
 static inline unsigned __ballot_sync(unsigned, bool p) { return plb_emu::warp_ballot(p); }
 static inline bool __all_sync(unsigned, bool p)
 {
-    return plb_emu::warp_ballot(p) == plb_emu::warp_active_mask();
+    unsigned active = 0;
+    const unsigned votes = plb_emu::warp_ballot(p, &active);
+    return votes == active;
 }
 static inline bool __any_sync(unsigned, bool p) { return plb_emu::warp_ballot(p) != 0; }
 template <typename T>

@@ -34,12 +34,15 @@ CASES = {
     "thin": lambda: cases.poiseuille(8, 21),
     # uneven ceil split (parallel/domain.py:54-66): 19 + 18, or 10 + 10 + 10 + 7
     "uneven": lambda: cases.cavity(37, 29),
+    # wide enough for fully deep warp strips in every slab (fused path)
+    "wide_channel": lambda: _mrt(cases.poiseuille(48, 140)),
+    "wide_cylinder": lambda: _centered(cases.cylinder(64, 131, radius=9)),
 }
 
 
 def _centered(sim):
     """Put the body on the slab cut (x = 32 of 64, two ranks)."""
-    sim.obstacle_dict["cyl"]["center"] = [32, 15]
+    sim.obstacle_dict["cyl"]["center"] = [32, sim.mesh_dict["grid"][1] // 2]
     return sim
 
 
@@ -70,10 +73,11 @@ def global_oracle(sim):
     return orc, st
 
 
-def run_one(comm, name, steps, strict, face, out_dir):
+def run_one(comm, name, steps, strict, face, out_dir, fuse="1"):
     """One decomposed run against the global oracle; returns 0 on parity."""
     rank, world = comm.Get_rank(), comm.Get_size()
     os.environ["PLB_FACE"] = face
+    os.environ["PLB_FUSE"] = fuse        # 2: two steps per pass on any lattice
     sim = CASES[name]()
     sim.decompose_dict = {"nx": world, "ny": 1}
     solver = Solver(comm, "b200", simulation=sim, strict=strict, verbose=False,
@@ -84,6 +88,7 @@ def run_one(comm, name, steps, strict, face, out_dir):
     solver.plb.initialize_pop()
     solver.advance(steps, store_moments_last=True)
     solver.plb.sync()
+    pairs = solver.plb.fused_info()["pairs"]
     got = solver.fields_to_host()
     shape = solver.state.domain.shape
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"),
@@ -101,6 +106,9 @@ def run_one(comm, name, steps, strict, face, out_dir):
     if rank == 0:
         tag = f"{name} x{world} {'strict' if strict else 'production'} {face}"
         want_transport = {"nccl": capi.FACES_NCCL, "p2p": capi.FACES_P2P}[face]
+        if fuse == "2" and pairs == 0:
+            print(f"[multirank] {tag}: the fused path did not run", flush=True)
+            status = 1
         if transport != want_transport:
             print(f"[multirank] {tag}: face transport {transport}, wanted "
                   f"{want_transport}", flush=True)
@@ -146,10 +154,11 @@ def main():
     comm = TorchComm()
     results = {}
     for spec in specs:
-        name, steps, mode, face = spec.split(":")
+        name, steps, mode, face, *rest = spec.split(":")
         try:
             results[spec] = run_one(comm, name, int(steps), mode == "strict",
-                                    face, out_dir)
+                                    face, out_dir,
+                                    fuse="2" if "fuse2" in rest else "1")
         except Exception as e:           # noqa: BLE001 -- report, then stop:
             print(f"[multirank] {spec}: {type(e).__name__}: {e}", flush=True)
             results[spec] = 2            # the ranks are no longer in step

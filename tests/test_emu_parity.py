@@ -1,0 +1,264 @@
+"""Kernel-logic tests without a GPU (test infrastructure, see tests/emu/README.md).
+
+The unchanged CUDA sources of libplb are compiled by g++ against a stand-in
+CUDA runtime whose kernel launches run the threads as cooperative fibers
+(warp shuffles, votes, __syncthreads), and the result is driven through the
+same C ABI and the same Python host as the GPU.  -ffp-contract=off gives the
+arithmetic of the -fmad=false build, so BGK paths must equal the reference's
+golden vectors bit for bit.  What is checked here is what needs no hardware:
+indexing, the shuffle-assembled 128-bit store patterns, warp-edge cases, the
+node classification, the list passes and the host-side ordering of the
+single-step path and of the two-steps-per-pass path (k_bulk_fused2 /
+step_pair).  The `-m gpu` tests remain the parity tests proper.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+from oracle.oracle import Oracle
+from pylabolt_b200 import capi
+from pylabolt_b200.comm import SingleComm
+from pylabolt_b200.solver import Solver
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import build_emu  # noqa: E402
+
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    return build_emu.build()
+
+
+@pytest.fixture
+def emu(emu_lib, monkeypatch):
+    """Routes THIS TEST's solvers to the emulated library (PLB_LIB is the
+    loader's explicit override; the product default never points here)."""
+    monkeypatch.setenv("PLB_LIB", emu_lib)
+    monkeypatch.delenv("PLB_FUSED_ROWS", raising=False)
+    monkeypatch.delenv("PLB_KERNEL", raising=False)
+    return monkeypatch
+
+
+def rel_err(a, b):
+    scale = np.abs(b).max()
+    return 0.0 if scale == 0 else float(np.abs(a - b).max() / scale)
+
+
+def make_solver(sim):
+    s = Solver(SingleComm(), "b200", simulation=sim, strict=True, verbose=False)
+    s.set_backend()
+    s.compile()
+    s.plb.initialize_pop()
+    return s
+
+
+def oracle_for(solver, n_threads=4):
+    st = solver.state
+    col = solver.collision_operator
+    elements = [{"type": el.type_fluid, "nodes": el.boundary_nodes,
+                 "out": el.out_list, "inv": el.inv_list, "normal": el.normal,
+                 "vector": el.vector_fluid, "scalar": float(el.scalar_fluid)}
+                for el in st.boundary.boundary_elements]
+    orc = Oracle(st.domain.shape, st.fields.solid, st.fields.ghost_node,
+                 st.fields.density, st.fields.velocity, elements,
+                 col.omega_fluid, gravity=solver.force_operator.gravity,
+                 forcing=col.forcing_fluid, collision=col.collision_fluid,
+                 x_periodic=st.boundary.x_periodic,
+                 y_periodic=st.boundary.y_periodic, mrt_rates=col.mrt_rates,
+                 n_threads=n_threads)
+    orc.initialize_pop()
+    return orc
+
+
+# PLB_FUSE: 0 = single steps only, 2 = two steps per pass wherever a deep node
+# exists (the default, 1, skips lattices as small as the golden ones)
+@pytest.mark.parametrize("fuse", ["0", "2"])
+@pytest.mark.parametrize("variant", ["vec2", "scalar"])
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN_CASES))
+def test_emulated_kernels_are_bit_exact_with_reference(golden_dir, emu, name,
+                                                       variant, fuse):
+    if fuse == "2" and variant == "scalar":
+        pytest.skip("the fused path has one kernel variant")
+    emu.setenv("PLB_KERNEL", variant)
+    emu.setenv("PLB_FUSE", fuse)
+    factory, kwargs, record = cases.GOLDEN_CASES[name]
+    data = np.load(os.path.join(golden_dir, name + ".npz"))
+    s = make_solver(factory(**kwargs))
+    try:
+        assert np.array_equal(s.plb.download(capi.POP), data["pop_0"])
+        done = 0
+        for step in record:
+            s.advance(step - done, store_moments_last=True)
+            done = step
+            got = s.fields_to_host()
+            assert np.array_equal(got["density"], data[f"density_{step}"]), step
+            assert np.array_equal(got["velocity"], data[f"velocity_{step}"]), step
+            assert np.array_equal(got["pop_fluid_new"], data[f"pop_{step}"]), step
+        info = s.plb.fused_info()
+        assert (info["pairs"] > 0) == (fuse == "2")
+    finally:
+        s.close()
+
+
+def _mrt(sim):
+    sim.collision_dict["fluid"]["model"] = "MRT"
+    return sim
+
+
+def _mrt_free_rates(sim):
+    sim.collision_dict["fluid"]["model"] = "MRT"
+    sim.collision_dict["fluid"]["mrt_rates"] = [1.0, 1.4, 1.3, 1.0, 1.2, 1.0,
+                                                1.2, 1.7, 1.6]
+    return sim
+
+
+def _zero_gradient_outlet(sim):
+    sim.boundary_dict["outlet"]["fluid"] = {"type": "zero_gradient"}
+    return sim
+
+
+# Lattices wide enough that whole 62-node strips are deep (the 128-bit store
+# path of the fused kernel), several strips, several row chunks, odd sizes,
+# the periodic seam, bodies, every collision / forcing model.
+WIDE_CASES = {
+    "poiseuille_70x140_guo2": lambda: cases.poiseuille(70, 140),
+    "poiseuille_33x190_guo1": lambda: cases.poiseuille(33, 190, forcing="guo_linear"),
+    "poiseuille_9x300_none": lambda: cases.poiseuille(9, 300, forcing=None),
+    "mrt_poiseuille_70x140_guo2": lambda: _mrt(cases.poiseuille(70, 140)),
+    "mrt_poiseuille_40x129_guo1": lambda: _mrt(cases.poiseuille(40, 129, forcing="guo_linear")),
+    "mrt_free_rates_45x131": lambda: _mrt_free_rates(cases.periodic_box(45, 131)),
+    "periodic_box_67x131": lambda: cases.periodic_box(67, 131),
+    "cavity_40x200": lambda: cases.cavity(40, 200),
+    "cylinder_120x140": lambda: cases.cylinder(120, 140),
+    "channel_y_140x40": lambda: cases.channel_y(140, 40),
+    "zero_gradient_100x127": lambda: _zero_gradient_outlet(cases.inflow_cylinder(100, 127)),
+    "mrt_zero_gradient_64x125": lambda: _mrt(_zero_gradient_outlet(cases.inflow_cylinder(64, 125))),
+    # degenerate: too thin for any deep node -> the pair path must stay off
+    "three_columns_periodic": lambda: cases.poiseuille(3, 140),
+    "two_rows_y_periodic": lambda: cases.channel_y(140, 2),
+}
+
+
+def _run(sim_factory, n_steps, fuse, emu, rows=None, one_by_one=False):
+    emu.setenv("PLB_FUSE", fuse)
+    if rows is None:
+        emu.delenv("PLB_FUSED_ROWS", raising=False)
+    else:
+        emu.setenv("PLB_FUSED_ROWS", str(rows))
+    s = make_solver(sim_factory())
+    try:
+        if one_by_one:
+            for _ in range(n_steps - 1):
+                s.execute_single_time_step()
+            s.single_time_step(store_moments=True)
+        else:
+            s.advance(n_steps, store_moments_last=True)
+        return s.fields_to_host(), s.plb.fused_info()
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("name", sorted(WIDE_CASES))
+def test_two_steps_per_pass_equals_two_single_steps(emu, name):
+    """Same per-node arithmetic, so the fused path must reproduce the
+    single-step path BIT FOR BIT (any collision model), for even and odd step
+    counts, for several chunk heights, and when the host issues one step per
+    call like the reference's Solver.run."""
+    factory = WIDE_CASES[name]
+    want, info0 = _run(factory, 13, "0", emu)
+    assert info0["pairs"] == 0
+    for rows, one_by_one in ((None, False), (5, False), (64, True)):
+        got, info = _run(factory, 13, "2", emu, rows=rows, one_by_one=one_by_one)
+        if info["n_deep"] == 0:
+            assert info["active"] == 0 and info["pairs"] == 0
+        else:
+            assert info["pairs"] == 6, info
+        for key in ("density", "velocity", "pop_fluid_new"):
+            assert np.array_equal(got[key], want[key]), (name, rows, key)
+
+
+@pytest.mark.parametrize("name", ["poiseuille_70x140_guo2", "cylinder_120x140",
+                                  "mrt_poiseuille_70x140_guo2",
+                                  "zero_gradient_100x127"])
+def test_fused_path_against_oracle(emu, name):
+    emu.setenv("PLB_FUSE", "2")
+    s = make_solver(WIDE_CASES[name]())
+    try:
+        orc = oracle_for(s)
+        for n in (2, 7, 16):
+            s.advance(n, store_moments_last=True)
+            orc.step(n)
+            got = s.fields_to_host()
+            assert rel_err(got["density"], orc.density) <= RTOL
+            assert rel_err(got["velocity"], orc.velocity) <= RTOL
+            assert rel_err(got["pop_fluid_new"], orc.pop_new) <= RTOL
+            bgk = s.collision_operator.collision_fluid == "BGK"
+            if bgk and "zero_gradient" not in name:
+                assert np.array_equal(got["pop_fluid_new"], orc.pop_new)
+        assert s.plb.fused_info()["pairs"] == (0 + 3 + 7)   # flagged last steps run unfused
+    finally:
+        s.close()
+
+
+def test_default_mode_pairs_only_where_deep_nodes_dominate(emu):
+    emu.delenv("PLB_FUSE", raising=False)
+    small = make_solver(cases.cavity())              # 33 x 29: list passes dominate
+    large = make_solver(cases.cavity(101, 101))      # BASELINE configs[0]
+    try:
+        assert small.plb.fused_info()["active"] == 0
+        info = large.plb.fused_info()
+        assert info["active"] == 1 and info["n_deep"] == 97 * 97
+        large.advance(10)
+        large.plb.sync()
+        assert large.plb.fused_info()["pairs"] == 5
+    finally:
+        small.close()
+        large.close()
+
+
+def test_held_back_step_is_completed_by_every_observer(emu):
+    """plb_step may hold one plain step back for pairing; download, sync,
+    residues and a flagged step must all see it done."""
+    emu.setenv("PLB_FUSE", "2")
+    factory = WIDE_CASES["poiseuille_70x140_guo2"]
+    want, _ = _run(factory, 5, "0", emu)
+    emu.setenv("PLB_FUSE", "2")
+    s = make_solver(factory())
+    try:
+        for _ in range(3):
+            s.plb.step(1)                     # 2 run as a pair, 1 is held back
+        assert s.plb.fused_info()["pairs"] == 1
+        pop3 = s.plb.download(capi.POP)       # completes the third step
+        s.plb.step(1)
+        s.plb.step(1, store_moments=True)     # flagged: runs 4 and 5 unfused
+        got = s.fields_to_host()
+        for key in ("density", "velocity", "pop_fluid_new"):
+            assert np.array_equal(got[key], want[key]), key
+        ref3, _ = _run(factory, 3, "0", emu)
+        assert np.array_equal(pop3, ref3["pop_fluid_new"])
+    finally:
+        s.close()
+
+
+def test_residues_and_link_record_with_pairing(emu):
+    emu.setenv("PLB_FUSE", "0")
+    a = make_solver(cases.cylinder(120, 140))
+    emu.setenv("PLB_FUSE", "2")
+    b = make_solver(cases.cylinder(120, 140))
+    try:
+        for s in (a, b):
+            s.advance(6, store_moments_last=True)
+            s.plb.residue_sums()
+            s.plb.step(5, store_moments=True, record_links=True)
+        assert np.array_equal(a.plb.residue_sums(), b.plb.residue_sums())
+        n = a.plb.info()["n_link"]
+        assert np.array_equal(a.plb.link_exchange(n), b.plb.link_exchange(n))
+        assert b.plb.fused_info()["pairs"] == 2 + 2
+    finally:
+        a.close()
+        b.close()

@@ -40,12 +40,24 @@ TWO_SLABS = ([f"{n}:25:strict:p2p" for n in NAMES] +
              [f"{n}:25:production:nccl" for n in NAMES] +
              ["periodic_box:25:production:p2p", "cylinder_cut:25:strict:nccl",
               "periodic_box:400:strict:p2p", "poiseuille:400:strict:nccl",
-              "thin:60:strict:p2p", "thin:60:strict:nccl"])
+              "thin:60:strict:p2p", "thin:60:strict:nccl"] +
+             # two steps per pass (PLB_FUSE=2): both transports, a body on the
+             # cut, the periodic seam through the ring, long runs
+             [f"{n}:25:strict:p2p:fuse2" for n in NAMES] +
+             ["cylinder_cut:26:strict:nccl:fuse2",
+              "periodic_box:400:strict:p2p:fuse2",
+              "poiseuille:401:strict:nccl:fuse2",
+              "wide_channel:41:production:p2p:fuse2",
+              "wide_cylinder:40:strict:p2p:fuse2",
+              "wide_channel:40:strict:nccl:fuse2"])
 FOUR_SLABS = ([f"{n}:25:strict:p2p" for n in
                ("poiseuille", "cylinder_cut", "periodic_box")] +
               ["periodic_box:25:strict:nccl", "mrt_box:300:production:p2p",
                "thin:60:strict:p2p", "thin:60:strict:nccl",
-               "uneven:40:strict:p2p"])
+               "uneven:40:strict:p2p", "uneven:41:strict:p2p:fuse2",
+               "periodic_box:25:strict:p2p:fuse2",
+               "wide_channel:60:strict:nccl:fuse2",
+               "wide_cylinder:60:strict:p2p:fuse2"])
 
 
 def _launch(world, specs, port):
