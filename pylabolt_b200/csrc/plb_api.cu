@@ -1089,9 +1089,12 @@ int plb_finalize_geometry(plb_handle s)
             if (const char *v = getenv("PLB_FUSED_ROWS")) {
                 s->fused_rows = std::max(1, atoi(v));
             } else {
-                // enough warps for ~6 waves of 148 SMs x 16 resident warps
-                const int64_t want = nx * fused_strips(L) / (148 * 16 * 6);
-                s->fused_rows = int32_t(std::min<int64_t>(128, std::max<int64_t>(16, want)));
+                // Short chunks measured best on B200 (profiles/: 32 rows beat 76,
+                // 128 and 512 although 2 of 34 row loads are then redundant):
+                // more warps are in their two-row prologue at any time, which
+                // puts more loads in flight.  Small lattices: >= 4 waves.
+                const int64_t want = nx * fused_strips(L) / (148 * 16 * 4);
+                s->fused_rows = int32_t(std::min<int64_t>(32, std::max<int64_t>(8, want)));
             }
         }
     }

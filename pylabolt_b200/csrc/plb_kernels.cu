@@ -309,30 +309,52 @@ constexpr int FUSED_SPAN = 62;
 #ifndef PLB_FUSED_MINBLOCKS
 #define PLB_FUSED_MINBLOCKS 4
 #endif
-// rows ahead that are prefetched into L2 (0: off)
-#ifndef PLB_FUSED_L2_AHEAD
-#define PLB_FUSED_L2_AHEAD 0
+// Row prefetch ring.  At 128 registers only 16 warps fit on an SM and ncu shows
+// them waiting on their row loads (long scoreboard: 6 of 10 cycles per issue),
+// so the rows are fetched AHEAD of their use with cp.async into a per-lane
+// shared-memory ring -- asynchronous copies need no destination registers.
+// PLB_FUSED_STAGES = slots of the ring (rows in flight + the one in use);
+// 0 = plain loads.  Every lane copies and later reads only its own 16 bytes
+// per population, so the ring needs no barrier, only cp.async.wait_group.
+#ifndef PLB_FUSED_STAGES
+#define PLB_FUSED_STAGES 2
 #endif
 
-// Stage 1 of one row: load the pair (y, y + 1), collide, and hand every
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+#ifdef PLB_EMU_RUNTIME
+    *static_cast<double2 *>(smem) = *static_cast<const double2 *>(gmem);
+#else
+    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem)
+                 : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+#ifndef PLB_EMU_RUNTIME
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+#ifndef PLB_EMU_RUNTIME
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// Stage 1 of one row: collide the pair (y, y + 1) and hand every
 // post-collision population to the lane that pulls it in the next step:
 // sa[k] is what node y receives in slot k, sb[k] what node y + 1 receives.
 // (For c_y = +1 lane 0's sa and for c_y = -1 lane 31's sb come from outside
 // the warp and are meaningless: those two nodes are not delivered.)
 template <int COLL, int FORCING>
-__device__ __forceinline__ void fused_stage1(const StepArgs &a, int64_t idx,
-                                             bool in_row, double sa[Q],
+__device__ __forceinline__ void fused_stage1(const StepArgs &a, const double fa[Q],
+                                             const double fb[Q], double sa[Q],
                                              double sb[Q])
 {
-    const int64_t plane = a.p.L.plane;
-    double fa[Q], fb[Q], ga[Q], gb[Q];
-#pragma unroll
-    for (int k = 0; k < Q; ++k) {
-        double2 v = make_double2(0.0, 0.0);
-        if (in_row) v = ld2(a.fin + k * plane + idx);
-        fa[k] = v.x;
-        fb[k] = v.y;
-    }
+    double ga[Q], gb[Q];
     collide<COLL, FORCING>(a.p, fa, ga);
     collide<COLL, FORCING>(a.p, fb, gb);
 #pragma unroll
@@ -368,44 +390,65 @@ k_bulk_fused2(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
     const bool in_row = L.y0 + y + 1 < L.pitch;
     const int64_t plane = L.plane, pitch = L.pitch;
 
-    // post-collision populations of earlier rows, shifted to their pullers
-    double pa[3], pb[3];   // row x - 1: k = 1, 5, 8
-    double na[3], nb[3];   // row x    : k = 1, 5, 8
-    double ca[3], cb[3];   // row x    : k = 0, 2, 4
-    {
-        double sa[Q], sb[Q];
-        fused_stage1<COLL, FORCING>(a, L.at(xs - 1, y), in_row, sa, sb);
-        pa[0] = sa[1]; pa[1] = sa[5]; pa[2] = sa[8];
-        pb[0] = sb[1]; pb[1] = sb[5]; pb[2] = sb[8];
-        fused_stage1<COLL, FORCING>(a, L.at(xs, y), in_row, sa, sb);
-        na[0] = sa[1]; na[1] = sa[5]; na[2] = sa[8];
-        nb[0] = sb[1]; nb[1] = sb[5]; nb[2] = sb[8];
-        ca[0] = sa[0]; ca[1] = sa[2]; ca[2] = sa[4];
-        cb[0] = sb[0]; cb[1] = sb[2]; cb[2] = sb[4];
-    }
-
-    for (int64_t x = xs; x < xe; ++x) {
-        const int64_t idx = L.at(x, y);
-#if PLB_FUSED_L2_AHEAD > 0 && !defined(PLB_EMU_RUNTIME)
-        if (in_row && ((lane & 7) == 0 || lane == 31) &&
-            x + 1 + PLB_FUSED_L2_AHEAD <= L.nx) {
-            const double *pf = a.fin + idx + (1 + PLB_FUSED_L2_AHEAD) * pitch;
+    // Rows xs - 1 .. xe go through stage 1 in order (row number i = 0 ..);
+    // from i = 2 on, row x = xs + i - 2 is complete and goes through stage 2.
+    const int n_rows = int(xe - xs) + 2;
+    const double *row0 = a.fin + L.at(xs - 1, y);          // pair of row i = 0
+#if PLB_FUSED_STAGES >= 2
+    constexpr int AHEAD = PLB_FUSED_STAGES - 1;
+    __shared__ double2 ring[PLB_FUSED_STAGES][Q][PLB_FUSED_BLOCK];
+#pragma unroll
+    for (int i = 0; i < AHEAD; ++i) {
+        if (in_row && i < n_rows) {
 #pragma unroll
             for (int k = 0; k < Q; ++k)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + k * plane));
+                cp_async16(&ring[i][k][threadIdx.x], row0 + k * plane + i * pitch);
+        }
+        cp_async_commit();
+    }
+#endif
+
+    // post-collision populations of earlier rows, shifted to their pullers
+    double pa[3] = {0, 0, 0}, pb[3] = {0, 0, 0};   // row x - 1: k = 1, 5, 8
+    double na[3] = {0, 0, 0}, nb[3] = {0, 0, 0};   // row x    : k = 1, 5, 8
+    double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};   // row x    : k = 0, 2, 4
+
+    for (int i = 0; i < n_rows; ++i) {
+        double fa[Q], fb[Q];
+#if PLB_FUSED_STAGES >= 2
+        {
+            // refill the slot that was read in the previous iteration
+            const int j = i + AHEAD;
+            if (in_row && j < n_rows) {
+#pragma unroll
+                for (int k = 0; k < Q; ++k)
+                    cp_async16(&ring[j % PLB_FUSED_STAGES][k][threadIdx.x],
+                               row0 + k * plane + j * pitch);
+            }
+            cp_async_commit();
+            cp_async_wait<AHEAD>();                 // row i has landed
+            const int slot = i % PLB_FUSED_STAGES;
+#pragma unroll
+            for (int k = 0; k < Q; ++k) {
+                double2 v = make_double2(0.0, 0.0);
+                if (in_row) v = ring[slot][k][threadIdx.x];
+                fa[k] = v.x;
+                fb[k] = v.y;
+            }
+        }
+#else
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+            double2 v = make_double2(0.0, 0.0);
+            if (in_row) v = ld2(row0 + k * plane + i * pitch);
+            fa[k] = v.x;
+            fb[k] = v.y;
         }
 #endif
-        uint16_t dd = 0;
-        if (in_row) dd = *reinterpret_cast<const uint16_t *>(deep + idx);
-        // a lane delivers node y unless it is lane 0, node y + 1 unless lane 31
-        const bool da = (dd & 0xff) != 0 && lane != 0;
-        const bool db = (dd >> 8) != 0 && lane != 31;
-
         double sa[Q], sb[Q];
-        fused_stage1<COLL, FORCING>(a, idx + pitch, in_row, sa, sb);
+        fused_stage1<COLL, FORCING>(a, fa, fb, sa, sb);
 
-        // time t + 1 populations of row x
-        double fa[Q], fb[Q], ha[Q], hb[Q];
+        // time t + 1 populations of row x = xs + i - 2 (meaningful from i = 2)
         fa[0] = ca[0]; fa[1] = pa[0]; fa[2] = ca[1]; fa[3] = sa[3]; fa[4] = ca[2];
         fa[5] = pa[1]; fa[6] = sa[6]; fa[7] = sa[7]; fa[8] = pa[2];
         fb[0] = cb[0]; fb[1] = pb[0]; fb[2] = cb[1]; fb[3] = sb[3]; fb[4] = cb[2];
@@ -419,8 +462,17 @@ k_bulk_fused2(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         nb[0] = sb[1]; nb[1] = sb[5]; nb[2] = sb[8];
         ca[0] = sa[0]; ca[1] = sa[2]; ca[2] = sa[4];
         cb[0] = sb[0]; cb[1] = sb[2]; cb[2] = sb[4];
+        if (i < 2) continue;
 
+        const int64_t idx = L.at(xs + i - 2, y);
+        uint16_t dd = 0;
+        if (in_row) dd = *reinterpret_cast<const uint16_t *>(deep + idx);
+        // a lane delivers node y unless it is lane 0, node y + 1 unless lane 31
+        const bool da = (dd & 0xff) != 0 && lane != 0;
+        const bool db = (dd >> 8) != 0 && lane != 31;
         if (!__any_sync(0xffffffffu, da || db)) continue;
+
+        double ha[Q], hb[Q];
         collide<COLL, FORCING>(a.p, fa, ha);
         collide<COLL, FORCING>(a.p, fb, hb);
 
@@ -856,6 +908,16 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
     const int64_t chunks = (x_end - x_begin + rows_per_chunk - 1) / rows_per_chunk;
     const int64_t warps = chunks * strips;
     constexpr int wpb = PLB_FUSED_BLOCK / 32;
+#if PLB_FUSED_STAGES >= 2 && !defined(PLB_EMU_RUNTIME)
+    // the prefetch ring wants shared memory, nothing here wants L1
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        cudaFuncSetAttribute(k_bulk_fused2<C, F>,
+                             cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+    }
+#endif
     PLB_LAUNCH(COOP, (k_bulk_fused2<C, F>), unsigned((warps + wpb - 1) / wpb),
                PLB_FUSED_BLOCK, st, a, deep, x_begin, x_end, strips,
                rows_per_chunk);

@@ -9,13 +9,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pylabolt_b200 import build  # noqa: E402
 
 VARIANTS = {
-    "mb3": ["-DPLB_FUSED_MINBLOCKS=3"],
-    "mb5": ["-DPLB_FUSED_MINBLOCKS=5"],
-    "mb4_pf2": ["-DPLB_FUSED_L2_AHEAD=2"],
-    "mb4_pf4": ["-DPLB_FUSED_L2_AHEAD=4"],
-    "mb3_pf2": ["-DPLB_FUSED_MINBLOCKS=3", "-DPLB_FUSED_L2_AHEAD=2"],
-    "blk64": ["-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=8"],
-    "blk256": ["-DPLB_FUSED_BLOCK=256", "-DPLB_FUSED_MINBLOCKS=2"],
+    # two-steps-per-pass kernel: prefetch ring depth, CTA size, occupancy
+    "s0": ["-DPLB_FUSED_STAGES=0"],
+    "s2_mb3": ["-DPLB_FUSED_STAGES=2", "-DPLB_FUSED_MINBLOCKS=3"],
+    "s2_b64": ["-DPLB_FUSED_STAGES=2", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=8"],
+    "s3_b64_mb7": ["-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=7"],
+    "s3_b64_mb6": ["-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=6"],
+    "s4_b64_mb5": ["-DPLB_FUSED_STAGES=4", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=5"],
+    "s4_b32_mb12": ["-DPLB_FUSED_STAGES=4", "-DPLB_FUSED_BLOCK=32", "-DPLB_FUSED_MINBLOCKS=12"],
 }
 
 if __name__ == "__main__":

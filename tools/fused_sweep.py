@@ -34,7 +34,8 @@ for collision, forcing in %(models)s:
     p.add_boundary_element("bounce_back", bottom, [4, 7, 8], [2, 5, 6], [0, 1])
     p.add_boundary_element("bounce_back", top, [2, 5, 6], [4, 7, 8], [0, -1])
     p.finalize_geometry()
-    rho = np.ones(size)
+    # a rough density field, so that a misplaced population changes the result
+    rho = 1.0 + 1e-3 * ((np.arange(size, dtype=np.int64) * 2654435761 %% 1024) / 1024.0)
     p.upload(capi.DENSITY, rho)
     del rho
     p.initialize_pop()
@@ -48,7 +49,14 @@ for collision, forcing in %(models)s:
     ms = p.event_elapsed_ms(0, 1) / steps
     kernel_ms, launches = p.profile_read()
     info = p.fused_info()
+    # every variant must leave the same field behind: hash of rho after two
+    # more (moment-storing) steps
+    p.step(2, store_moments=True)
+    import hashlib
+    digest = hashlib.blake2b(p.download(capi.DENSITY_INNER).tobytes(),
+                             digest_size=6).hexdigest()
     out[f"{collision}/{forcing}"] = {
+        "hash": digest,
         "glups": round(nx * ny / (ms * 1e-3) / 1e9, 2),
         "kernel_share": round(kernel_ms / (ms * steps), 3),
         "pairs": info["pairs"], "rows": info["rows"]}
@@ -86,7 +94,8 @@ def main():
             continue
         res = json.loads(proc.stdout.strip().splitlines()[-1])
         cells = "  ".join(f"{k}: {v['glups']:6.2f} GLUPS (kernel share "
-                          f"{v['kernel_share']}, pairs {v['pairs']}, rows {v['rows']})"
+                          f"{v['kernel_share']}, pairs {v['pairs']}, rows {v['rows']}, "
+                          f"rho hash {v['hash']})"
                           for k, v in res.items())
         print(f"{tag:44s} {cells}", flush=True)
 
