@@ -320,6 +320,18 @@ constexpr int FUSED_SPAN = 62;
 #define PLB_FUSED_STAGES 2
 #endif
 
+// Resident CTAs per SM asked of ptxas, per collision model (PLB_FUSED_MINBLOCKS
+// for all, PLB_FUSED_MINBLOCKS_BGK for the reference-ordered BGK kernels, which
+// need more registers than the two-stress-moment MRT).
+__host__ __device__ constexpr int fused_min_blocks(int coll)
+{
+#ifdef PLB_FUSED_MINBLOCKS_BGK
+    return coll == 0 ? PLB_FUSED_MINBLOCKS_BGK : PLB_FUSED_MINBLOCKS;
+#else
+    return PLB_FUSED_MINBLOCKS;
+#endif
+}
+
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
 #ifdef PLB_EMU_RUNTIME
@@ -373,7 +385,7 @@ __device__ __forceinline__ void fused_stage1(const StepArgs &a, const double fa[
 }
 
 template <int COLL, int FORCING>
-__global__ void __launch_bounds__(PLB_FUSED_BLOCK, PLB_FUSED_MINBLOCKS)
+__global__ void __launch_bounds__(PLB_FUSED_BLOCK, fused_min_blocks(COLL))
 k_bulk_fused2(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
               int64_t x_end, int32_t strips, int32_t rows_per_chunk)
 {
@@ -413,7 +425,13 @@ k_bulk_fused2(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
     double na[3] = {0, 0, 0}, nb[3] = {0, 0, 0};   // row x    : k = 1, 5, 8
     double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};   // row x    : k = 0, 2, 4
 
+    // deep flags of the row that goes through stage 2 in the NEXT iteration:
+    // fetched one iteration ahead, so that the vote below never waits for them
+    uint16_t dd_next = 0;
     for (int i = 0; i < n_rows; ++i) {
+        const uint16_t dd = dd_next;
+        if (in_row && i >= 1 && i + 1 < n_rows)
+            dd_next = *reinterpret_cast<const uint16_t *>(deep + L.at(xs + i - 1, y));
         double fa[Q], fb[Q];
 #if PLB_FUSED_STAGES >= 2
         {
@@ -465,8 +483,6 @@ k_bulk_fused2(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         if (i < 2) continue;
 
         const int64_t idx = L.at(xs + i - 2, y);
-        uint16_t dd = 0;
-        if (in_row) dd = *reinterpret_cast<const uint16_t *>(deep + idx);
         // a lane delivers node y unless it is lane 0, node y + 1 unless lane 31
         const bool da = (dd & 0xff) != 0 && lane != 0;
         const bool db = (dd >> 8) != 0 && lane != 31;

@@ -12,11 +12,8 @@ VARIANTS = {
     # two-steps-per-pass kernel: prefetch ring depth, CTA size, occupancy
     "s0": ["-DPLB_FUSED_STAGES=0"],
     "s2_mb3": ["-DPLB_FUSED_STAGES=2", "-DPLB_FUSED_MINBLOCKS=3"],
-    "s2_b64": ["-DPLB_FUSED_STAGES=2", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=8"],
-    "s3_b64_mb7": ["-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=7"],
     "s3_b64_mb6": ["-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=6"],
-    "s4_b64_mb5": ["-DPLB_FUSED_STAGES=4", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=5"],
-    "s4_b32_mb12": ["-DPLB_FUSED_STAGES=4", "-DPLB_FUSED_BLOCK=32", "-DPLB_FUSED_MINBLOCKS=12"],
+    "bgk_mb3": ["-DPLB_FUSED_MINBLOCKS_BGK=3"],
 }
 
 if __name__ == "__main__":
