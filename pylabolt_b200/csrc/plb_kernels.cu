@@ -306,8 +306,13 @@ constexpr int FUSED_SPAN = 62;
 #ifndef PLB_FUSED_BLOCK
 #define PLB_FUSED_BLOCK 128
 #endif
+// Three CTAs of 128 threads per SM: 168 registers, nothing spills.  Measured on
+// B200 (profiles/r01_fused_sweep_v3_deepflags.txt): 82.0 GLUPS (MRT + Guo) /
+// 81.7 (BGK) against 70 / 64 at four CTAs (128 registers, spills in the loop)
+// and 52 at five; without the prefetch ring 12 warps would not hide the
+// row-load latency, with it they do.
 #ifndef PLB_FUSED_MINBLOCKS
-#define PLB_FUSED_MINBLOCKS 4
+#define PLB_FUSED_MINBLOCKS 3
 #endif
 // Row prefetch ring.  At 128 registers only 16 warps fit on an SM and ncu shows
 // them waiting on their row loads (long scoreboard: 6 of 10 cycles per issue),
