@@ -28,7 +28,7 @@
 #define PLB_UNPAREN(...) __VA_ARGS__
 #ifdef PLB_EMU_RUNTIME
 #define PLB_LAUNCH(MODE, KERNEL, GRID, BLOCK, STREAM, ...)                    \
-    PLB_EMU_LAUNCH(MODE, (PLB_UNPAREN KERNEL), GRID, BLOCK, __VA_ARGS__)
+    PLB_EMU_LAUNCH(MODE, (PLB_UNPAREN KERNEL), GRID, BLOCK, STREAM, __VA_ARGS__)
 #else
 #define PLB_LAUNCH(MODE, KERNEL, GRID, BLOCK, STREAM, ...)                    \
     PLB_UNPAREN KERNEL<<<(GRID), (BLOCK), 0, (STREAM)>>>(__VA_ARGS__)
@@ -1002,7 +1002,7 @@ int launch_face_unpack(const Layout &L, double *fout, int64_t x_col,
                        unsigned long long wait_value, unsigned long long *status,
                        long long spin_budget)
 {
-    PLB_LAUNCH(SIMPLE, (k_face_unpack), unsigned((L.ny + 255) / 256), 256, stream, L, fout, x_col, dirs[0], dirs[1], dirs[2], src, src_stride0, src_stride1, src_stride2, mask, wait_flag, wait_value, status, spin_budget);
+    PLB_LAUNCH(COOP, (k_face_unpack), unsigned((L.ny + 255) / 256), 256, stream, L, fout, x_col, dirs[0], dirs[1], dirs[2], src, src_stride0, src_stride1, src_stride2, mask, wait_flag, wait_value, status, spin_budget);
     return 1;
 }
 

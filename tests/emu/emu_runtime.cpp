@@ -1,81 +1,33 @@
 // TEST INFRASTRUCTURE (see include/cuda_runtime.h): the host-side stand-in for
-// the CUDA runtime and the fiber scheduler behind simt.h.
+// the CUDA runtime, the fiber executor behind simt.h, and an in-process
+// stand-in for the few NCCL calls libplb makes.
+//
+// Streams are queues of operations (kernel launches, copies, event records /
+// waits, sends / receives).  Whoever touches the runtime "pumps": it executes
+// the head of every queue until nothing can make progress.  An operation can
+// be BLOCKED -- an event that has not fired, a receive whose message has not
+// been sent, a kernel that spins on a flag another rank has not raised yet --
+// and then simply stays at the head of its queue.  That is all it takes to run
+// several ranks (one host thread each, like one process each on the GPU box)
+// in one process: a rank that synchronises while its neighbour has not issued
+// its step yet waits on a condition variable until the neighbour's thread
+// enqueues the work and pumps.  A wait that nobody ends is reported as a dead
+// lock instead of hanging the test.
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
 #include <ucontext.h>
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <nccl.h>
 
-// ===========================================================================
-// "runtime": device memory is host memory, a stream runs in issue order
-// ===========================================================================
-struct plb_emu_stream { int id; };
-struct plb_emu_event { int id; };
-
-extern "C" {
-
-const char *cudaGetErrorString(cudaError_t e)
-{
-    return e == cudaSuccess ? "no error"
-         : e == cudaErrorMemoryAllocation ? "out of memory"
-         : e == cudaErrorNotSupported ? "not supported by the emulator"
-         : "error";
-}
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
-cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
-cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 1000000; return cudaSuccess; }
-cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -1; return cudaSuccess; }
-cudaError_t cudaDeviceGetPCIBusId(char *buf, int len, int)
-{
-    snprintf(buf, size_t(len), "0000:00:00.0");
-    return cudaSuccess;
-}
-cudaError_t plb_emu_malloc(void **p, size_t n)
-{
-    // uninitialised on purpose (0xA5 pattern): reading memory nobody wrote
-    // shows up as a wild value, like on the device
-    *p = malloc(n ? n : 1);
-    if (!*p) return cudaErrorMemoryAllocation;
-    memset(*p, 0xA5, n);
-    return cudaSuccess;
-}
-cudaError_t plb_emu_host_alloc(void **p, size_t n)
-{
-    *p = malloc(n ? n : 1);
-    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
-}
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
-cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
-cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
-cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t)
-{
-    memmove(d, s, n);
-    return cudaSuccess;
-}
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new plb_emu_stream{0}; return cudaSuccess; }
-cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = new plb_emu_stream{1}; return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
-cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new plb_emu_event{0}; return cudaSuccess; }
-cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new plb_emu_event{0}; return cudaSuccess; }
-cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return cudaSuccess; }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
-
-}  // extern "C"
-
-// ===========================================================================
-// SIMT fibers
-// ===========================================================================
 namespace plb_emu {
 
 uint3 g_threadIdx = {0, 0, 0}, g_blockIdx = {0, 0, 0};
@@ -83,6 +35,101 @@ dim3 g_blockDim(1, 1, 1), g_gridDim(1, 1, 1);
 
 namespace {
 
+std::mutex g_mu;                       // one big lock: the "device"
+std::condition_variable g_cv;          // "something made progress"
+using Lock = std::unique_lock<std::mutex>;
+constexpr int DEADLOCK_SECONDS = 90;
+
+[[noreturn]] void die(const char *what)
+{
+    fprintf(stderr, "plb_emu: %s (block %u, thread %u)\n", what, g_blockIdx.x,
+            g_threadIdx.x);
+    abort();
+}
+
+// ---------------------------------------------------------------------------
+// operations and streams
+// ---------------------------------------------------------------------------
+struct Op {
+    virtual ~Op() {}
+    virtual bool run() = 0;            // false: blocked, try again later
+};
+
+}  // namespace
+}  // namespace plb_emu
+
+struct plb_emu_stream {
+    std::deque<std::unique_ptr<plb_emu::Op>> q;
+};
+struct plb_emu_event {
+    unsigned long long enqueued = 0, done = 0;   // sequence numbers of records
+};
+
+namespace plb_emu {
+namespace {
+
+std::vector<plb_emu_stream *> g_streams;
+unsigned long long g_seq = 0;
+
+// Executes queue heads until nothing moves.  Caller holds the lock.
+bool pump()
+{
+    bool any = false, progress = true;
+    while (progress) {
+        progress = false;
+        for (size_t i = 0; i < g_streams.size(); ++i) {
+            plb_emu_stream *s = g_streams[i];
+            while (!s->q.empty()) {
+                if (!s->q.front()->run()) break;
+                s->q.pop_front();
+                progress = any = true;
+            }
+        }
+    }
+    if (any) g_cv.notify_all();
+    return any;
+}
+
+// Blocks the calling host thread until pred() holds, pumping in between.
+template <typename Pred>
+void host_wait(Lock &lk, Pred pred, const char *what)
+{
+    auto last_progress = std::chrono::steady_clock::now();
+    for (;;) {
+        if (pump()) last_progress = std::chrono::steady_clock::now();
+        if (pred()) return;
+        if (g_cv.wait_for(lk, std::chrono::milliseconds(50)) == std::cv_status::no_timeout)
+            last_progress = std::chrono::steady_clock::now();
+        if (std::chrono::steady_clock::now() - last_progress >
+            std::chrono::seconds(DEADLOCK_SECONDS)) {
+            fprintf(stderr, "plb_emu: dead lock while waiting for %s\n", what);
+            abort();
+        }
+    }
+}
+
+void enqueue(plb_emu_stream *s, Op *op)
+{
+    Lock lk(g_mu);
+    if (!s) {                            // legacy default stream: right now
+        std::unique_ptr<Op> own(op);
+        host_wait(lk, [&] { return own->run(); }, "an operation on the default stream");
+        return;
+    }
+    s->q.emplace_back(op);
+    pump();
+    g_cv.notify_all();
+}
+
+struct FnOp : Op {
+    std::function<bool()> fn;
+    explicit FnOp(std::function<bool()> f) : fn(std::move(f)) {}
+    bool run() override { return fn(); }
+};
+
+// ---------------------------------------------------------------------------
+// SIMT fibers
+// ---------------------------------------------------------------------------
 constexpr int MAX_THREADS = 1024;
 constexpr size_t STACK_BYTES = size_t(256) << 10;
 
@@ -90,14 +137,13 @@ struct Barrier {
     int count = 0;
     unsigned gen = 0;
 };
-
 struct Fiber {
     ucontext_t ctx;
     char *stack = nullptr;
     bool done = true;
 };
 
-bool g_coop = false;
+bool g_coop = false, g_blocked = false;
 int g_n = 0, g_cur = 0;
 int g_alive_block = 0, g_alive_warp[MAX_THREADS / 32];
 Barrier g_block_barrier, g_warp_barrier[MAX_THREADS / 32];
@@ -107,13 +153,6 @@ Fiber g_fiber[MAX_THREADS];
 ucontext_t g_sched;
 const std::function<void()> *g_body = nullptr;
 long long g_idle = 0, g_ticks = 0;
-
-[[noreturn]] void die(const char *what)
-{
-    fprintf(stderr, "plb_emu: %s (block %u, thread %u)\n", what, g_blockIdx.x,
-            g_threadIdx.x);
-    abort();
-}
 
 void yield()
 {
@@ -152,7 +191,82 @@ void need_coop(const char *what)
     if (!g_coop) die(what);
 }
 
+// One block; false if a thread of it went to sleep on a condition that only
+// other work can change (the block is abandoned and will be run again).
+bool run_block(int mode, unsigned b, dim3 block, const std::function<void()> &body)
+{
+    g_blockIdx = uint3{b, 0, 0};
+    g_blocked = false;
+    if (mode == SIMPLE) {
+        g_coop = false;
+        for (unsigned t = 0; t < block.x; ++t) {
+            g_threadIdx = uint3{t, 0, 0};
+            body();
+        }
+        return true;
+    }
+    g_coop = true;
+    g_n = int(block.x);
+    g_body = &body;
+    g_alive_block = g_n;
+    g_block_barrier = Barrier();
+    for (int w = 0; w < (g_n + 31) / 32; ++w) {
+        g_alive_warp[w] = (g_n - w * 32 < 32) ? g_n - w * 32 : 32;
+        g_warp_barrier[w] = Barrier();
+    }
+    for (int t = 0; t < g_n; ++t) {
+        Fiber &f = g_fiber[t];
+        if (!f.stack) f.stack = static_cast<char *>(malloc(STACK_BYTES));
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = STACK_BYTES;
+        f.ctx.uc_link = &g_sched;
+        f.done = false;
+        makecontext(&f.ctx, trampoline, 0);
+    }
+    g_idle = 0;
+    while (g_alive_block > 0 && !g_blocked) {
+        for (int t = 0; t < g_n && !g_blocked; ++t) {
+            if (g_fiber[t].done) continue;
+            g_cur = t;
+            g_threadIdx = uint3{unsigned(t), 0, 0};
+            swapcontext(&g_sched, &g_fiber[t].ctx);
+        }
+    }
+    g_coop = false;
+    return !g_blocked;
+}
+
+struct LaunchOp : Op {
+    int mode;
+    dim3 grid, block;
+    std::function<void()> body;
+    unsigned next_block = 0;
+    bool run() override
+    {
+        g_gridDim = grid;
+        g_blockDim = block;
+        for (; next_block < grid.x; ++next_block)
+            if (!run_block(mode, next_block, block, body)) return false;
+        return true;
+    }
+};
+
 }  // namespace
+
+void launch(int mode, dim3 grid, dim3 block, cudaStream_t stream,
+            std::function<void()> body)
+{
+    if (grid.y != 1 || grid.z != 1 || block.y != 1 || block.z != 1)
+        die("only one-dimensional launches are emulated");
+    if (block.x < 1 || block.x > unsigned(MAX_THREADS)) die("bad block size");
+    LaunchOp *op = new LaunchOp();
+    op->mode = mode;
+    op->grid = grid;
+    op->block = block;
+    op->body = std::move(body);
+    enqueue(stream, op);
+}
 
 void sync_block()
 {
@@ -206,53 +320,337 @@ unsigned warp_ballot(bool pred, unsigned *active)
 
 long long clock_ticks() { return g_ticks += 1000; }
 
-void launch(int mode, dim3 grid, dim3 block, const std::function<void()> &body)
+// A kernel thread sleeps because it polls memory that only other work (another
+// rank's kernels) can change: give the block up, the launch is retried later.
+void sleep_hook()
 {
-    if (grid.y != 1 || grid.z != 1 || block.y != 1 || block.z != 1)
-        die("only one-dimensional launches are emulated");
-    if (block.x < 1 || block.x > unsigned(MAX_THREADS)) die("bad block size");
-    g_gridDim = grid;
-    g_blockDim = block;
-    for (unsigned b = 0; b < grid.x; ++b) {
-        g_blockIdx = uint3{b, 0, 0};
-        if (mode == SIMPLE) {
-            g_coop = false;
-            for (unsigned t = 0; t < block.x; ++t) {
-                g_threadIdx = uint3{t, 0, 0};
-                body();
-            }
-            continue;
-        }
-        g_coop = true;
-        g_n = int(block.x);
-        g_body = &body;
-        g_alive_block = g_n;
-        g_block_barrier = Barrier();
-        for (int w = 0; w < (g_n + 31) / 32; ++w) {
-            g_alive_warp[w] = (g_n - w * 32 < 32) ? g_n - w * 32 : 32;
-            g_warp_barrier[w] = Barrier();
-        }
-        for (int t = 0; t < g_n; ++t) {
-            Fiber &f = g_fiber[t];
-            if (!f.stack) f.stack = static_cast<char *>(malloc(STACK_BYTES));
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack;
-            f.ctx.uc_stack.ss_size = STACK_BYTES;
-            f.ctx.uc_link = &g_sched;
-            f.done = false;
-            makecontext(&f.ctx, trampoline, 0);
-        }
-        g_idle = 0;
-        while (g_alive_block > 0) {
-            for (int t = 0; t < g_n; ++t) {
-                if (g_fiber[t].done) continue;
-                g_cur = t;
-                g_threadIdx = uint3{unsigned(t), 0, 0};
-                swapcontext(&g_sched, &g_fiber[t].ctx);
-            }
-        }
-        g_coop = false;
-    }
+    need_coop("__nanosleep (a polling kernel) in a kernel launched in SIMPLE mode");
+    g_blocked = true;
+    swapcontext(&g_fiber[g_cur].ctx, &g_sched);
+    die("an abandoned fiber was resumed");
 }
 
 }  // namespace plb_emu
+
+using plb_emu::enqueue;
+using plb_emu::FnOp;
+using plb_emu::g_mu;
+using plb_emu::Lock;
+
+// ===========================================================================
+// "runtime": device memory is host memory
+// ===========================================================================
+extern "C" {
+
+const char *cudaGetErrorString(cudaError_t e)
+{
+    return e == cudaSuccess ? "no error"
+         : e == cudaErrorMemoryAllocation ? "out of memory"
+         : e == cudaErrorNotSupported ? "not supported by the emulator"
+         : "error";
+}
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int *n) { *n = 8; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 1000000; return cudaSuccess; }
+cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -1; return cudaSuccess; }
+cudaError_t cudaDeviceGetPCIBusId(char *buf, int len, int)
+{
+    snprintf(buf, size_t(len), "0000:00:00.0");
+    return cudaSuccess;
+}
+cudaError_t plb_emu_malloc(void **p, size_t n)
+{
+    // uninitialised on purpose (0xA5 pattern): reading memory nobody wrote
+    // shows up as a wild value, like on the device
+    *p = malloc(n ? n : 1);
+    if (!*p) return cudaErrorMemoryAllocation;
+    memset(*p, 0xA5, n);
+    return cudaSuccess;
+}
+cudaError_t plb_emu_host_alloc(void **p, size_t n)
+{
+    *p = malloc(n ? n : 1);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFree(void *p)
+{
+    {
+        Lock lk(g_mu);
+        plb_emu::pump();
+    }
+    free(p);
+    return cudaSuccess;
+}
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemset(void *p, int v, size_t n)
+{
+    Lock lk(g_mu);
+    plb_emu::pump();
+    memset(p, v, n);
+    return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t s)
+{
+    enqueue(s, new FnOp([=] { memset(p, v, n); return true; }));
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind)
+{
+    Lock lk(g_mu);
+    plb_emu::pump();
+    memmove(d, s, n);
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t st)
+{
+    enqueue(st, new FnOp([=] { memmove(d, s, n); return true; }));
+    return cudaSuccess;
+}
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned)
+{
+    Lock lk(g_mu);
+    *s = new plb_emu_stream();
+    plb_emu::g_streams.push_back(*s);
+    return cudaSuccess;
+}
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned f, int)
+{
+    return cudaStreamCreateWithFlags(s, f);
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t s)
+{
+    if (!s) return cudaSuccess;
+    Lock lk(g_mu);
+    plb_emu::host_wait(lk, [&] { return s->q.empty(); }, "cudaStreamSynchronize");
+    return cudaSuccess;
+}
+cudaError_t cudaStreamDestroy(cudaStream_t s)
+{
+    cudaStreamSynchronize(s);
+    Lock lk(g_mu);
+    auto &v = plb_emu::g_streams;
+    for (size_t i = 0; i < v.size(); ++i)
+        if (v[i] == s) { v.erase(v.begin() + long(i)); break; }
+    delete s;
+    return cudaSuccess;
+}
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new plb_emu_event(); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+// events are never freed: an operation still queued may refer to one
+cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s)
+{
+    unsigned long long seq;
+    {
+        Lock lk(g_mu);
+        seq = e->enqueued = ++plb_emu::g_seq;
+    }
+    enqueue(s, new FnOp([=] { e->done = seq; return true; }));
+    return cudaSuccess;
+}
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned)
+{
+    unsigned long long target;
+    {
+        Lock lk(g_mu);
+        target = e->enqueued;
+    }
+    if (target) enqueue(s, new FnOp([=] { return e->done >= target; }));
+    return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t e)
+{
+    Lock lk(g_mu);
+    plb_emu::host_wait(lk, [&] { return e->done >= e->enqueued; }, "cudaEventSynchronize");
+    return cudaSuccess;
+}
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return cudaSuccess; }
+// "IPC": every rank lives in this address space, the handle is the pointer
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p)
+{
+    if (getenv("PLB_EMU_NO_IPC")) return cudaErrorNotSupported;
+    memset(h, 0, sizeof *h);
+    memcpy(h->reserved, &p, sizeof p);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned)
+{
+    memcpy(p, h.reserved, sizeof *p);
+    return *p ? cudaSuccess : cudaErrorInvalidValue;
+}
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+
+}  // extern "C"
+
+// ===========================================================================
+// NCCL stand-in: ranks are host threads of this process
+// ===========================================================================
+namespace {
+
+struct Message {
+    std::vector<char> bytes;
+};
+struct Group {
+    int n = 0, joined = 0;
+    std::map<std::pair<int, int>, std::deque<Message>> mail;   // (src, dst) -> FIFO
+    struct Reduce {
+        int arrived = 0, left = 0;
+        std::vector<std::vector<char>> parts;
+    };
+    std::map<unsigned long long, Reduce> reductions;
+};
+std::map<std::string, Group *> g_groups;
+
+size_t type_size(ncclDataType_t t)
+{
+    return t == ncclChar ? 1 : t == ncclInt ? 4 : 8;
+}
+
+struct PendingP2p {
+    bool send;
+    const void *src;
+    void *dst;
+    size_t bytes;
+    int peer;
+    ncclComm_t comm;
+    cudaStream_t stream;
+};
+thread_local int t_group_depth = 0;
+thread_local std::vector<PendingP2p> t_pending;
+
+}  // namespace
+
+struct ncclComm {
+    Group *group;
+    int rank;
+    unsigned long long reduce_seq = 0;
+};
+
+namespace {
+
+void issue(const PendingP2p &p)
+{
+    Group *g = p.comm->group;
+    const int me = p.comm->rank;
+    if (p.send) {
+        enqueue(p.stream, new FnOp([=] {
+            Message m;
+            m.bytes.assign(static_cast<const char *>(p.src),
+                           static_cast<const char *>(p.src) + p.bytes);
+            g->mail[{me, p.peer}].push_back(std::move(m));
+            return true;
+        }));
+    } else {
+        enqueue(p.stream, new FnOp([=] {
+            auto &box = g->mail[{p.peer, me}];
+            if (box.empty()) return false;               // not sent yet
+            if (box.front().bytes.size() != p.bytes)
+                plb_emu::die("ncclRecv size differs from the matching ncclSend");
+            memcpy(p.dst, box.front().bytes.data(), p.bytes);
+            box.pop_front();
+            return true;
+        }));
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+ncclResult_t ncclGetUniqueId(ncclUniqueId *id)
+{
+    static unsigned long long counter = 0;
+    Lock lk(g_mu);
+    memset(id, 0, sizeof *id);
+    snprintf(id->internal, sizeof id->internal, "plb-emu-%llu", ++counter);
+    return ncclSuccess;
+}
+ncclResult_t ncclCommInitRank(ncclComm_t *comm, int n, ncclUniqueId id, int rank)
+{
+    Lock lk(g_mu);
+    Group *&g = g_groups[std::string(id.internal)];
+    if (!g) {
+        g = new Group();
+        g->n = n;
+    }
+    ++g->joined;
+    plb_emu::g_cv.notify_all();
+    Group *group = g;
+    plb_emu::host_wait(lk, [&] { return group->joined >= group->n; }, "ncclCommInitRank");
+    *comm = new ncclComm{group, rank};
+    return ncclSuccess;
+}
+ncclResult_t ncclCommDestroy(ncclComm_t) { return ncclSuccess; }
+ncclResult_t ncclGroupStart(void) { ++t_group_depth; return ncclSuccess; }
+// inside a group all sends are issued before the receives, like NCCL, which
+// progresses the operations of a group together
+ncclResult_t ncclGroupEnd(void)
+{
+    if (--t_group_depth > 0) return ncclSuccess;
+    std::vector<PendingP2p> ops;
+    ops.swap(t_pending);
+    for (const PendingP2p &p : ops) if (p.send) issue(p);
+    for (const PendingP2p &p : ops) if (!p.send) issue(p);
+    return ncclSuccess;
+}
+ncclResult_t ncclSend(const void *buf, size_t count, ncclDataType_t t, int peer,
+                      ncclComm_t comm, cudaStream_t s)
+{
+    PendingP2p p{true, buf, nullptr, count * type_size(t), peer, comm, s};
+    if (t_group_depth > 0) t_pending.push_back(p);
+    else issue(p);
+    return ncclSuccess;
+}
+ncclResult_t ncclRecv(void *buf, size_t count, ncclDataType_t t, int peer,
+                      ncclComm_t comm, cudaStream_t s)
+{
+    PendingP2p p{false, nullptr, buf, count * type_size(t), peer, comm, s};
+    if (t_group_depth > 0) t_pending.push_back(p);
+    else issue(p);
+    return ncclSuccess;
+}
+ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataType_t t,
+                           ncclRedOp_t op, ncclComm_t comm, cudaStream_t s)
+{
+    if (t != ncclInt && t != ncclDouble) return ncclUnhandledCudaError;
+    Group *g = comm->group;
+    const unsigned long long seq = comm->reduce_seq++;
+    const size_t bytes = count * type_size(t);
+    auto deposited = std::make_shared<bool>(false);
+    enqueue(s, new FnOp([=] {
+        Group::Reduce &r = g->reductions[seq];
+        if (!*deposited) {
+            r.parts.emplace_back(static_cast<const char *>(send),
+                                 static_cast<const char *>(send) + bytes);
+            ++r.arrived;
+            r.left = g->n;
+            *deposited = true;
+        }
+        if (r.arrived < g->n) return false;
+        for (size_t i = 0; i < count; ++i) {
+            if (t == ncclInt) {
+                int acc = 0;
+                for (int k = 0; k < g->n; ++k) {
+                    int v;
+                    memcpy(&v, r.parts[size_t(k)].data() + 4 * i, 4);
+                    acc = k == 0 ? v : (op == ncclMin ? (v < acc ? v : acc) : acc + v);
+                }
+                memcpy(static_cast<char *>(recv) + 4 * i, &acc, 4);
+            } else {
+                double acc = 0;
+                for (int k = 0; k < g->n; ++k) {
+                    double v;
+                    memcpy(&v, r.parts[size_t(k)].data() + 8 * i, 8);
+                    acc = k == 0 ? v : (op == ncclMin ? (v < acc ? v : acc) : acc + v);
+                }
+                memcpy(static_cast<char *>(recv) + 8 * i, &acc, 8);
+            }
+        }
+        return true;
+    }));
+    return ncclSuccess;
+}
+const char *ncclGetErrorString(ncclResult_t r) { return r == ncclSuccess ? "no error" : "error"; }
+
+}  // extern "C"

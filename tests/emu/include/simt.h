@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <tuple>
 
 namespace plb_emu {
 
@@ -17,7 +18,11 @@ extern uint3 g_threadIdx, g_blockIdx;
 extern dim3 g_blockDim, g_gridDim;
 
 enum LaunchMode { SIMPLE = 0, COOP = 1 };
-void launch(int mode, dim3 grid, dim3 block, const std::function<void()> &body);
+// Enqueues the launch on `stream` (null: runs it now); `body` is called once
+// per thread with threadIdx / blockIdx set.
+void launch(int mode, dim3 grid, dim3 block, cudaStream_t stream,
+            std::function<void()> body);
+void sleep_hook();
 
 void sync_block();
 void sync_warp();
@@ -52,9 +57,12 @@ inline T from_bits(uint64_t b)
 #define gridDim (plb_emu::g_gridDim)
 
 // launch macro of the kernels' translation unit (PLB_LAUNCH in plb_kernels.cu)
-#define PLB_EMU_LAUNCH(mode, kernel, grid, block, ...)                         \
-    plb_emu::launch(plb_emu::mode, dim3(grid), dim3(block),                    \
-                    [&]() { kernel(__VA_ARGS__); })
+// (arguments are evaluated and copied NOW, the kernel may run later)
+#define PLB_EMU_LAUNCH(mode, kernel, grid, block, stream, ...)                 \
+    plb_emu::launch(plb_emu::mode, dim3(grid), dim3(block), stream,            \
+                    [plb_emu_args = std::make_tuple(__VA_ARGS__)]() {          \
+                        std::apply(kernel, plb_emu_args);                      \
+                    })
 
 // ---- device intrinsics used by the kernels -----------------------------------
 static inline void __syncthreads() { plb_emu::sync_block(); }
@@ -94,7 +102,7 @@ static inline T __ldcs(const T *p) { return *p; }
 template <typename T>
 static inline void __stcs(T *p, T v) { *p = v; }
 static inline long long clock64() { return plb_emu::clock_ticks(); }
-static inline void __nanosleep(unsigned) {}
+static inline void __nanosleep(unsigned) { plb_emu::sleep_hook(); }
 static inline void __threadfence_system() {}
 static inline void __threadfence() {}
 static inline unsigned long long atomicExch(unsigned long long *p,
