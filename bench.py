@@ -345,7 +345,7 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device):
     plb.profile_enable(True)
     plb.sync()
     comm.Barrier()
-    pairs_before = plb.fused_info()["pairs"]
+    groups_before = (plb.fused_info()["pairs"], plb.fused_info()["triples"])
     sampler.mark_start()
     plb.event_record(0)
     plb.step(steps, False)
@@ -367,20 +367,24 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device):
     # roofline of the dominant kernel (bulk collide-stream), this rank.
     # Algorithmic bytes = 144 B per node and step x the
     # node-steps a launch advances: the single-step kernel advances its bulk
-    # nodes by one step, k_bulk_fused2 its deep nodes by TWO steps while it
+    # nodes by one step, k_bulk_fused its deep nodes by TWO (three) steps while it
     # reads and writes each population once -- 72 B of DRAM traffic per node
     # and step, which is how `achieved` can exceed the HBM peak; `dram_gbs`
     # is the same launch measured in bytes that really cross HBM.
     peak, peak_src = hbm_peak()
     finfo = plb.fused_info()
-    pairs = finfo["pairs"] - pairs_before
-    singles = steps - 2 * pairs
+    pairs = finfo["pairs"] - groups_before[0]
+    triples = finfo["triples"] - groups_before[1]
+    singles = steps - 2 * pairs - 3 * triples
     bulk_ms_per_step = bulk_ms / steps
-    node_steps = 2 * finfo["n_deep"] * pairs + info["n_bulk_timed"] * singles
-    dram_nodes = finfo["n_deep"] * pairs + info["n_bulk_timed"] * singles
+    node_steps = (2 * finfo["n_deep"] * pairs + 3 * finfo["n_deep3"] * triples +
+                  info["n_bulk_timed"] * singles)
+    dram_nodes = (finfo["n_deep"] * pairs + finfo["n_deep3"] * triples +
+                  info["n_bulk_timed"] * singles)
     achieved = ALGORITHMIC_BYTES_PER_NODE * node_steps / (bulk_ms * 1e-3) / 1e9
-    fused = pairs > 0
-    kernel = ("k_bulk_fused2" if fused else
+    fused = pairs + triples > 0
+    kernel = ("k_bulk_fused<depth 3>" if triples else
+              "k_bulk_fused<depth 2>" if pairs else
               "k_bulk_vec2" if info["variant"] else "k_bulk_scalar")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
@@ -388,14 +392,14 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device):
                 "kernel": kernel,
                 "algorithmic_bytes_per_launch":
                     ALGORITHMIC_BYTES_PER_NODE * node_steps / max(1, bulk_n),
-                "steps_per_launch": 2 if fused else 1,
+                "steps_per_launch": 3 if triples else 2 if pairs else 1,
                 "dram_gbs": ALGORITHMIC_BYTES_PER_NODE * dram_nodes /
                             (bulk_ms * 1e-3) / 1e9,
                 "dram_frac": ALGORITHMIC_BYTES_PER_NODE * dram_nodes /
                              (bulk_ms * 1e-3) / 1e9 / peak,
-                "fused": {k: finfo[k] for k in ("active", "n_deep", "n_list1",
-                                                "n_list2", "rows", "strips")},
-                "pairs": pairs, "single_steps": singles,
+                "fused": {k: finfo[k] for k in ("active", "n_deep", "n_deep3",
+                                                "n_list1", "rows", "strips")},
+                "pairs": pairs, "triples": triples, "single_steps": singles,
                 "face_transport": ["none", "own ghost rows", "nccl",
                                    "p2p stores"][info["faces"]],
                 "launches_per_step": bulk_n / steps,

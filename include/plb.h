@@ -147,18 +147,22 @@ int plb_initialize_pop(plb_handle h);
 #define PLB_RECORD_LINKS 2
 int plb_step(plb_handle h, int64_t n_steps, int32_t flags);
 int plb_sync(plb_handle h);
-/* Two steps per pass.  Steps that need neither flag are advanced two at a
+/* Several steps per pass.  Steps that need neither flag are advanced two at a
  * time where the geometry allows it: nodes whose whole neighbourhood is plain
  * fluid go through both steps in registers (lattice read once, written once:
  * 72 B per node and step instead of 144), all other nodes through two
  * ordinary passes hidden behind that kernel.  The result is the one of two
  * single steps (same per-node arithmetic).  Because plb_step() is
- * asynchronous, a single plain step may be held back until its partner
- * arrives; every other entry point first completes what was held back.
- * PLB_FUSE=0 in the environment disables the path, PLB_FUSE=2 uses it on any
- * lattice that has such nodes (default: lattices where they dominate).
- * out = {active, deep nodes, nodes of list pass 1, of list pass 2,
- *        pairs executed, rows per warp chunk, y strips, PLB_FUSE mode} */
+ * asynchronous, plain steps that do not fill a group may be held back until
+ * the rest arrives; every other entry point first completes what was held
+ * back.  Environment: PLB_FUSE=0 disables the path, PLB_FUSE=2 uses it on any
+ * lattice that has such nodes (default: lattices where they dominate);
+ * PLB_FUSE_DEPTH=3 groups three steps (48 B per node and step; nodes whose
+ * neighbourhood of radius two is plain fluid; opt-in).
+ * out = {steps per pass in use (0: off), nodes advanced by the two-step kernel,
+ *        by the three-step kernel, nodes of the first list pass,
+ *        two-step passes executed, rows per warp chunk, y strips,
+ *        three-step passes executed} */
 int plb_fused_info(plb_handle h, int64_t out[8]);
 
 /* ---- diagnostics ("next" rows) ----------------------------------------- */

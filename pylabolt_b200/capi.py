@@ -339,8 +339,8 @@ class Plb:
         """State of the two-steps-per-pass path (plb_fused_info)."""
         out = (ctypes.c_int64 * 8)()
         self._check(self.lib.plb_fused_info(self._h, out))
-        keys = ("active", "n_deep", "n_list1", "n_list2", "pairs", "rows",
-                "strips", "mode")
+        keys = ("active", "n_deep", "n_deep3", "n_list1", "pairs", "rows",
+                "strips", "triples")
         return dict(zip(keys, out[:8]))
 
     def copy_bandwidth(self):

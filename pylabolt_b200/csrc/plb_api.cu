@@ -162,17 +162,22 @@ struct plb_solver {
     unsigned char *peer_left = nullptr, *peer_right = nullptr;   // their xbuf
     long long spin_budget = 0;
 
-    // Two steps per pass (step_pair): PLB_FUSE = 0 off, 1 when the geometry
-    // qualifies (default), 2 whenever there is a deep node at all.
+    // Several steps per pass (step_fused): PLB_FUSE = 0 off, 1 when the
+    // geometry qualifies (default), 2 whenever there is a deep node at all;
+    // PLB_FUSE_DEPTH = steps per pass (2, or 3: opt-in until measured).
     int fuse_mode = PLB_FUSE_DEFAULT;
-    bool fused_ok = false;
-    double *f_mid = nullptr;             // scratch lattice (lazy)
-    uint8_t *deep_dev = nullptr;         // 1 = bulk node with eight bulk neighbours
-    LinkNode *list1_dev = nullptr, *list2_dev = nullptr;
-    int64_t n_list1 = 0, n_list2 = 0, n_deep = 0;
-    int32_t fused_rows = 64;             // rows a warp marches over (PLB_FUSED_ROWS)
-    int64_t pending = 0;                 // plain steps held back for pairing
-    int64_t pairs_done = 0;
+    int fuse_depth = 2;
+    int fused_depth_ok = 0;              // largest depth the geometry qualifies for (0: none)
+    double *f_mid[2] = {nullptr, nullptr};   // scratch lattices (lazy)
+    uint8_t *deep_dev = nullptr;         // distance to the nearest non-bulk node - 1, capped at 2
+    // list p (0-based) = nodes of list pass p + 1 of a depth-d group,
+    // lists[d - 2][p]; the last one holds the fluid nodes that are not deep enough
+    LinkNode *lists_dev[2][3] = {};
+    int64_t n_lists[2][3] = {};
+    int64_t n_deep[2] = {0, 0};          // nodes the depth-2 / depth-3 kernel advances
+    int32_t fused_rows = 32;             // rows a warp marches over (PLB_FUSED_ROWS)
+    int64_t pending = 0;                 // plain steps held back for grouping
+    int64_t groups_done[2] = {0, 0};
 
     int64_t launches = 0;
     int64_t steps_done = 0;
@@ -546,48 +551,54 @@ int step_once(plb_solver *s, bool store, bool record)
     return PLB_OK;
 }
 
-// Two steps as one pass (k_bulk_fused2 in plb_kernels.cu).  A = time t,
-// B = time t + 2, M = a scratch lattice that holds time t + 1 on the nodes
-// that are NOT deep:
-//   edge stream: step t+1 on list 1 (the non-deep fluid nodes and the deep
-//                nodes next to them) A -> M, faces, zero_gradient on M;
-//                step t+2 on list 2 (the non-deep fluid nodes) M -> B, faces;
-//   main stream: both steps of every deep node, A -> B;
+// DEPTH (2 or 3) steps as one pass (k_bulk_fused in plb_kernels.cu).  A = time t,
+// B = time t + DEPTH, M1 (M2) = scratch lattices that hold time t + 1 (t + 2)
+// on the nodes that are NOT deep enough:
+//   edge stream: list pass 1: A -> M1 (-> ... -> B in the last pass), each with
+//                its face exchange and, except the last, its zero_gradient pass;
+//                list p holds the not-deep-enough fluid nodes plus the deep
+//                nodes within distance DEPTH - p of them (they feed the next
+//                pass);
+//   main stream: all DEPTH steps of every deep node, A -> B;
 //   join, zero_gradient on B.
 // Slot (n, k) of B has one writer: the owner n - c_k (deep: the fused kernel,
-// else the second list pass), n itself (bounce back / element / uncovered
-// ghost), or the face delivery.  Every slot of M that the second list pass
-// reads (all nine of every non-deep fluid node) is written by the first one:
-// its source is a non-deep node, a deep node next to a non-deep one (both on
-// list 1), the node itself, or the face delivery.  The per-step protocol
-// between ranks (stores, mailbox value t, delivery) is the one of step_once,
-// so a neighbour may run the same two steps unfused.
-int step_pair(plb_solver *s)
+// else the last list pass), n itself (bounce back / element / uncovered
+// ghost), or the face delivery.  Every slot of a scratch lattice that the next
+// list pass reads (all nine of each of its nodes) is written by the pass
+// before: its source is on that pass's (larger) list, the node itself, or the
+// face delivery.  The per-step protocol between ranks (stores, mailbox value
+// t, delivery) is the one of step_once, so a neighbour may run the same steps
+// unfused.
+int step_fused(plb_solver *s, int depth)
 {
     const Layout &L = s->L;
-    if (!s->f_mid) {
+    for (int m = 0; m < depth - 1; ++m) {
+        if (s->f_mid[m]) continue;
         const size_t bytes = size_t(Q) * L.plane * sizeof(double);
-        if (cudaMalloc(&s->f_mid, bytes) != cudaSuccess) {
+        if (cudaMalloc(&s->f_mid[m], bytes) != cudaSuccess) {
             cudaGetLastError();
-            s->f_mid = nullptr;
-            s->fused_ok = false;       // no room for the scratch lattice
+            s->f_mid[m] = nullptr;
+            // no room for the scratch lattice: fall back to what fits
+            s->fused_depth_ok = m == 0 ? 0 : 2;
             return PLB_ERR_NOMEM;
         }
-        CUDA_TRY(cudaMemsetAsync(s->f_mid, 0, bytes, s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->f_mid[m], 0, bytes, s->stream));
     }
-    double *A = s->f[s->cur], *B = s->f[s->cur ^ 1], *M = s->f_mid;
+    double *A = s->f[s->cur], *B = s->f[s->cur ^ 1];
     cudaStream_t es = s->edge_stream;
     CUDA_TRY(cudaEventRecord(s->ev_edge, s->stream));
     CUDA_TRY(cudaStreamWaitEvent(es, s->ev_edge, 0));
     const unsigned long long t1 = (unsigned long long)(s->steps_done + 1);
     int64_t x_lo = 0, x_hi = 0;
-    if (int rc = edge_chain(s, step_args(s, A, M), t1, s->list1_dev, s->n_list1, false,
-                            &x_lo, &x_hi))
-        return rc;
-    run_zero_gradient(s, M, es);
-    if (int rc = edge_chain(s, step_args(s, M, B), t1 + 1, s->list2_dev, s->n_list2,
-                            false, &x_lo, &x_hi))
-        return rc;
+    for (int p = 0; p < depth; ++p) {
+        const double *fin = p == 0 ? A : s->f_mid[p - 1];
+        double *fout = p == depth - 1 ? B : s->f_mid[p];
+        if (int rc = edge_chain(s, step_args(s, fin, fout), t1 + p,
+                                s->lists_dev[depth - 2][p], s->n_lists[depth - 2][p],
+                                false, &x_lo, &x_hi))
+            return rc;
+        if (p < depth - 1) run_zero_gradient(s, fout, es);
+    }
     CUDA_TRY(cudaEventRecord(s->ev_comm, es));
 
     const StepArgs a = step_args(s, A, B);
@@ -601,7 +612,8 @@ int step_pair(plb_solver *s)
             }
         CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used], s->stream));
     }
-    s->launches += launch_bulk_fused(a, s->deep_dev, 0, L.nx, s->fused_rows, s->stream);
+    s->launches += launch_bulk_fused(a, s->deep_dev, depth, 0, L.nx, s->fused_rows,
+                                     s->stream);
     if (prof) {
         CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used + 1], s->stream));
         s->prof_used += 2;
@@ -609,27 +621,35 @@ int step_pair(plb_solver *s)
     CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
     run_zero_gradient(s, B, s->stream);
     s->cur ^= 1;
-    s->steps_done += 2;
-    s->pairs_done += 1;
+    s->steps_done += depth;
+    s->groups_done[depth - 2] += 1;
     return PLB_OK;
 }
 
-bool fused_active(const plb_solver *s)
+// Steps per pass the solver groups plain steps into right now (1: none).
+int fused_depth(const plb_solver *s)
 {
-    return s->fused_ok && s->fuse_mode != 0;
+    if (s->fuse_mode == 0) return 1;
+    const int d = std::min(s->fuse_depth, s->fused_depth_ok);
+    return d >= 2 ? d : 1;
 }
 
+bool fused_active(const plb_solver *s) { return fused_depth(s) >= 2; }
+
 // n steps; `flags` apply to the last one.  Steps that need neither moments nor
-// the link record go two at a time when the fused path is active.
+// the link record go fused_depth() at a time (a remainder of two as a pair).
 int run_steps(plb_solver *s, int64_t n, int32_t flags)
 {
     int64_t i = 0;
     const int64_t plain = flags ? n - 1 : n;
-    while (fused_active(s) && plain - i >= 2) {
-        const int rc = step_pair(s);
-        if (rc == PLB_ERR_NOMEM && !s->fused_ok) break;   // fall through unfused
+    for (;;) {
+        int d = fused_depth(s);
+        if (d > plain - i) d = (plain - i >= 2 && fused_depth(s) >= 2) ? 2 : 1;
+        if (d < 2) break;
+        const int rc = step_fused(s, d);
+        if (rc == PLB_ERR_NOMEM) continue;      // fused_depth() has shrunk
         if (rc) return rc;
-        i += 2;
+        i += d;
     }
     for (; i < n; ++i) {
         const bool last = i == n - 1;
@@ -813,6 +833,8 @@ int plb_create(const plb_config *c, plb_handle *out)
         s->variant = (strcmp(v, "scalar") == 0) ? 0 : 1;
     if (const char *v = getenv("PLB_FUSE")) s->fuse_mode = atoi(v);
     if (s->fuse_mode < 0 || s->fuse_mode > 2) s->fuse_mode = PLB_FUSE_DEFAULT;
+    if (const char *v = getenv("PLB_FUSE_DEPTH")) s->fuse_depth = atoi(v);
+    if (s->fuse_depth < 2 || s->fuse_depth > 3) s->fuse_depth = 2;
     s->kernel_collision = c->collision;
     if (c->collision == PLB_MRT) {
         // S = (1,..,1,s7,s8) as in base/collision_operator.py:159-163 needs
@@ -871,10 +893,10 @@ void plb_destroy(plb_handle s)
     close_p2p(s);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (int i = 0; i < 2; ++i) cudaFree(s->f[i]);
-    cudaFree(s->f_mid);
+    for (int m = 0; m < 2; ++m) cudaFree(s->f_mid[m]);
     cudaFree(s->deep_dev);
-    cudaFree(s->list1_dev);
-    cudaFree(s->list2_dev);
+    for (int d = 0; d < 2; ++d)
+        for (int p = 0; p < 3; ++p) cudaFree(s->lists_dev[d][p]);
     cudaFree(s->mom);
     cudaFree(s->mom_old);
     cudaFree(s->res_partials);
@@ -1032,68 +1054,109 @@ int plb_finalize_geometry(plb_handle s)
         }
     }
 
-    // Two-steps-per-pass mode: DEEP nodes (bulk, all eight neighbours bulk) are
-    // advanced by k_bulk_fused2; list 2 holds every other fluid node, list 1
-    // additionally the deep nodes that push into one of those (step_pair).
-    {
+    // Several steps per pass: deep[n] = 1 if n and its eight neighbours are bulk
+    // nodes, 2 if all 24 nodes within distance two are (capped there).  A
+    // depth-d group advances the nodes with deep >= d - 1 in k_bulk_fused and
+    // everything else in d list passes: the last list holds the fluid nodes
+    // that are not deep enough, each earlier one adds the deep nodes that
+    // touch the list after it (step_fused).
+    if (s->fuse_mode != 0) {
         std::vector<uint8_t> deep(size_t(L.plane), 0);
         const int64_t P = L.pitch;
-        int64_t n_deep = 0;
+        auto all9 = [P](const uint8_t *c, int64_t y, uint8_t want) {
+            return c[y] == want && c[y - 1] == want && c[y + 1] == want &&
+                   c[y - P] == want && c[y - P - 1] == want && c[y - P + 1] == want &&
+                   c[y + P] == want && c[y + P - 1] == want && c[y + P + 1] == want;
+        };
         for (int64_t x = 1; x + 1 < nx; ++x) {
             const uint8_t *c = code.data() + L.at(x, 0);
             uint8_t *d = deep.data() + L.at(x, 0);
-            for (int64_t y = 1; y + 1 < ny; ++y) {
-                const uint8_t any = c[y] | c[y - 1] | c[y + 1] | c[y - P] | c[y - P - 1] |
-                                    c[y - P + 1] | c[y + P] | c[y + P - 1] | c[y + P + 1];
-                d[y] = any == NODE_BULK;
-                n_deep += d[y];
+            for (int64_t y = 1; y + 1 < ny; ++y) d[y] = all9(c, y, NODE_BULK);
+        }
+        {
+            std::vector<uint8_t> one(deep);
+            for (int64_t x = 2; x + 2 < nx; ++x) {
+                const uint8_t *o = one.data() + L.at(x, 0);
+                uint8_t *d = deep.data() + L.at(x, 0);
+                for (int64_t y = 2; y + 2 < ny; ++y)
+                    if (all9(o, y, 1)) d[y] = 2;
             }
         }
-        std::vector<LinkNode> list1, list2;
-        size_t next_link = 0;
-        for (int64_t x = 0; x < nx; ++x) {
-            const uint8_t *c = code.data() + L.at(x, 0);
-            const uint8_t *d = deep.data() + L.at(x, 0);
-            for (int64_t y = 0; y < ny; ++y) {
-                if (c[y] == NODE_LINK) {
-                    const LinkNode &ln = link_nodes[next_link++];   // same (x, y) order
-                    list1.push_back(ln);
-                    list2.push_back(ln);
-                } else if (c[y] == NODE_BULK && !d[y]) {
-                    list1.push_back(LinkNode{int32_t(x), int32_t(y), 0});
-                    list2.push_back(LinkNode{int32_t(x), int32_t(y), 0});
-                } else if (c[y] == NODE_BULK) {
-                    // deep: all eight neighbours are bulk; on list 1 if one is not deep
-                    const bool ring = !(d[y - 1] & d[y + 1] & d[y - P] & d[y - P - 1] &
-                                        d[y - P + 1] & d[y + P] & d[y + P - 1] &
-                                        d[y + P + 1]);
-                    if (ring) list1.push_back(LinkNode{int32_t(x), int32_t(y), 0});
+        const int64_t n_fluid = n_bulk + int64_t(link_nodes.size());
+        std::vector<uint8_t> on_list(size_t(L.plane), 0), next(size_t(L.plane), 0);
+        for (int depth = 2; depth <= 3; ++depth) {
+            const uint8_t need = uint8_t(depth - 1);
+            int64_t n_deep = 0;
+            // last list: fluid nodes that are not deep enough
+            std::fill(on_list.begin(), on_list.end(), 0);
+            for (int64_t x = 0; x < nx; ++x) {
+                const uint8_t *c = code.data() + L.at(x, 0);
+                const uint8_t *d = deep.data() + L.at(x, 0);
+                uint8_t *o = on_list.data() + L.at(x, 0);
+                for (int64_t y = 0; y < ny; ++y) {
+                    const bool fluid = c[y] == NODE_BULK || c[y] == NODE_LINK;
+                    o[y] = fluid && d[y] < need;
+                    n_deep += fluid && d[y] >= need;
                 }
             }
+            std::vector<std::vector<LinkNode>> lists;
+            lists.resize(size_t(depth));
+            for (int p = depth - 1; p >= 0; --p) {
+                size_t next_link = 0;
+                for (int64_t x = 0; x < nx; ++x) {
+                    const uint8_t *c = code.data() + L.at(x, 0);
+                    const uint8_t *o = on_list.data() + L.at(x, 0);
+                    for (int64_t y = 0; y < ny; ++y) {
+                        if (c[y] == NODE_LINK) {
+                            const LinkNode &ln = link_nodes[next_link++];   // same (x, y) order
+                            lists[size_t(p)].push_back(ln);
+                        } else if (o[y]) {
+                            lists[size_t(p)].push_back(LinkNode{int32_t(x), int32_t(y), 0});
+                        }
+                    }
+                }
+                if (p == 0) break;
+                // the list before: add the deep nodes next to this one (they
+                // are bulk nodes with bulk neighbours, so x, y are interior)
+                next = on_list;
+                for (int64_t x = 1; x + 1 < nx; ++x) {
+                    const uint8_t *o = on_list.data() + L.at(x, 0);
+                    const uint8_t *d = deep.data() + L.at(x, 0);
+                    uint8_t *nn = next.data() + L.at(x, 0);
+                    for (int64_t y = 1; y + 1 < ny; ++y)
+                        if (!o[y] && d[y] >= need &&
+                            (o[y - 1] | o[y + 1] | o[y - P] | o[y - P - 1] | o[y - P + 1] |
+                             o[y + P] | o[y + P - 1] | o[y + P + 1]))
+                            nn[y] = 1;
+                }
+                on_list.swap(next);
+            }
+            s->n_deep[depth - 2] = n_deep;
+            const bool ok = n_deep > 0 &&
+                            (s->fuse_mode == 2 ||
+                             (int64_t(lists[0].size()) * 8 <= n_fluid && n_fluid >= 4096));
+            if (!ok || depth > s->fuse_depth) continue;
+            s->fused_depth_ok = depth;
+            for (int p = 0; p < depth; ++p) {
+                const std::vector<LinkNode> &l = lists[size_t(p)];
+                s->n_lists[depth - 2][p] = int64_t(l.size());
+                CUDA_TRY(cudaMalloc(&s->lists_dev[depth - 2][p],
+                                    std::max<size_t>(1, l.size()) * sizeof(LinkNode)));
+                CUDA_TRY(cudaMemcpy(s->lists_dev[depth - 2][p], l.data(),
+                                    l.size() * sizeof(LinkNode), cudaMemcpyHostToDevice));
+            }
         }
-        s->n_deep = n_deep;
-        s->n_list1 = int64_t(list1.size());
-        s->n_list2 = int64_t(list2.size());
-        const int64_t n_fluid = n_bulk + int64_t(link_nodes.size());
-        s->fused_ok = n_deep > 0 &&
-                      (s->fuse_mode == 2 || (s->n_list1 * 8 <= n_fluid && n_fluid >= 4096));
-        if (s->fused_ok && s->fuse_mode != 0) {
+        if (s->fused_depth_ok >= 2) {
             CUDA_TRY(cudaMalloc(&s->deep_dev, deep.size()));
             CUDA_TRY(cudaMemcpy(s->deep_dev, deep.data(), deep.size(), cudaMemcpyHostToDevice));
-            CUDA_TRY(cudaMalloc(&s->list1_dev, std::max<size_t>(1, list1.size()) * sizeof(LinkNode)));
-            CUDA_TRY(cudaMemcpy(s->list1_dev, list1.data(), list1.size() * sizeof(LinkNode),
-                                cudaMemcpyHostToDevice));
-            CUDA_TRY(cudaMalloc(&s->list2_dev, std::max<size_t>(1, list2.size()) * sizeof(LinkNode)));
-            CUDA_TRY(cudaMemcpy(s->list2_dev, list2.data(), list2.size() * sizeof(LinkNode),
-                                cudaMemcpyHostToDevice));
             if (const char *v = getenv("PLB_FUSED_ROWS")) {
                 s->fused_rows = std::max(1, atoi(v));
             } else {
                 // Short chunks measured best on B200 (profiles/: 32 rows beat 76,
                 // 128 and 512 although 2 of 34 row loads are then redundant):
-                // more warps are in their two-row prologue at any time, which
-                // puts more loads in flight.  Small lattices: >= 4 waves.
-                const int64_t want = nx * fused_strips(L) / (148 * 16 * 4);
+                // more warps are in their prologue at any time, which puts more
+                // loads in flight.  Small lattices: >= 4 waves.
+                const int64_t want = nx * fused_strips(L, 2) / (148 * 16 * 4);
                 s->fused_rows = int32_t(std::min<int64_t>(32, std::max<int64_t>(8, want)));
             }
         }
@@ -1232,10 +1295,11 @@ int plb_step(plb_handle s, int64_t n_steps, int32_t flags)
     flags &= PLB_STORE_MOMENTS | PLB_RECORD_LINKS;
     int64_t n = s->pending + n_steps;
     s->pending = 0;
-    if (fused_active(s) && flags == 0 && (n & 1)) {
-        // an odd plain step waits for its partner (flush_pending)
-        s->pending = 1;
-        n -= 1;
+    if (fused_active(s) && flags == 0) {
+        // plain steps that do not fill a group wait for the rest of it
+        // (flush_pending)
+        s->pending = n % fused_depth(s);
+        n -= s->pending;
     }
     if (int rc = run_steps(s, n, flags)) return rc;
     CUDA_TRY(cudaGetLastError());
@@ -1245,14 +1309,15 @@ int plb_step(plb_handle s, int64_t n_steps, int32_t flags)
 int plb_fused_info(plb_handle s, int64_t out[8])
 {
     if (!s || !out) return fail(PLB_ERR_INVALID, "null argument");
-    out[0] = fused_active(s) ? 1 : 0;
-    out[1] = s->n_deep;
-    out[2] = s->n_list1;
-    out[3] = s->n_list2;
-    out[4] = s->pairs_done;
+    const int d = fused_depth(s);
+    out[0] = d >= 2 ? d : 0;
+    out[1] = s->n_deep[0];
+    out[2] = s->n_deep[1];
+    out[3] = d >= 2 ? s->n_lists[d - 2][0] : 0;
+    out[4] = s->groups_done[0];
     out[5] = s->fused_rows;
-    out[6] = fused_strips(s->L);
-    out[7] = s->fuse_mode;
+    out[6] = fused_strips(s->L, d >= 2 ? d : 2);
+    out[7] = s->groups_done[1];
     return PLB_OK;
 }
 

@@ -111,11 +111,14 @@ struct StepArgs {
 // All return the number of kernels launched (0 if nothing to do).
 int launch_bulk(const StepArgs &a, int64_t x_begin, int64_t x_end, int variant,
                 cudaStream_t stream);
-// Two steps in one pass over the DEEP nodes of columns [x_begin, x_end)
-// (fin = time t, fout = time t + 2); `deep` is one byte per node.
-int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
-                      int64_t x_end, int32_t rows_per_chunk, cudaStream_t stream);
-int fused_strips(const Layout &L);
+// `depth` (2 or 3) steps in one pass over the nodes of columns [x_begin, x_end)
+// whose deep[] value is >= depth - 1 (fin = time t, fout = time t + depth);
+// deep[] is one byte per node: the Chebyshev distance up to which all
+// neighbours are bulk nodes, capped at 2.
+int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
+                      int64_t x_begin, int64_t x_end, int32_t rows_per_chunk,
+                      cudaStream_t stream);
+int fused_strips(const Layout &L, int depth);
 // One slab-edge column with the face redirection of StepArgs::face_lo/hi.
 int launch_bulk_edge(const StepArgs &a, int64_t x_begin, int64_t x_end,
                      cudaStream_t stream);

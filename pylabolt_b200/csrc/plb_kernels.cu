@@ -278,31 +278,34 @@ k_bulk_vec2(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
 // two time steps in one pass (temporal blocking in registers)
 // ---------------------------------------------------------------------------
 // The single-step kernels above move 144 B per node and step and run at the
-// HBM roofline; the only way past it is to touch HBM less.  k_bulk_fused2
-// advances DEEP nodes (bulk nodes whose eight neighbours are bulk nodes too,
-// `deep` plane) by TWO steps per pass: lattice A (time t) is read once,
-// lattice B (time t + 2) is written once, 72 B per node and step.  The
-// intermediate lattice (time t + 1) never exists in memory:
+// HBM roofline; the only way past it is to touch HBM less.  k_bulk_fused
+// advances DEEP nodes by DEPTH = 2 (or 3) steps per pass: lattice A (time t)
+// is read once, lattice B (time t + DEPTH) is written once, 144 / DEPTH bytes
+// per node and step.  The intermediate lattices never exist in memory:
 //
 //   * a warp owns a strip of 64 consecutive y (two per lane, 128-bit loads) and
-//     marches along x; row r is loaded and collided once ("stage 1"), and its
+//     marches along x; a row is loaded and collided once ("level 0"), and its
 //     post-collision populations are kept in registers, already shifted in y
 //     (one shuffle per population with c_y != 0) to the lane that PULLS them;
-//   * the time-(t+1) state of row x is then complete in registers: k = 1, 5, 8
-//     came from row x - 1 (two iterations old), k = 0, 2, 4 from row x (one
-//     iteration old), k = 3, 6, 7 from row x + 1 (fresh).  It is collided again
-//     ("stage 2") and pushed into B exactly like k_bulk_vec2 pushes;
-//   * the two outer nodes of the strip have no y-neighbour inside the warp, so
-//     a warp delivers FUSED_SPAN = 62 of its 64 nodes and strips overlap by two
-//     (3 % redundant stage-1 work, the overlapped loads hit L2); chunks of
-//     rows overlap by two rows in x.  No shared memory, no block barrier.
+//   * the time-(t+1) state of the row before it is then complete in registers:
+//     k = 1, 5, 8 came from two rows back (two iterations old), k = 0, 2, 4
+//     from one row back (one iteration old), k = 3, 6, 7 are fresh.  It is
+//     collided again; with DEPTH = 3 the same hand-over happens once more, one
+//     row further back; the last collision is pushed into B exactly like
+//     k_bulk_vec2 pushes;
+//   * every hand-over costs the strip its two outer nodes (no y-neighbour
+//     inside the warp), so a warp delivers 62 (60) of its 64 nodes and strips
+//     overlap by two (four); chunks of rows overlap by two (four) rows in x.
+//     The overlapped loads hit L2.  No block barrier anywhere.
 //
-// Every node that is not deep (domain edges, obstacle surfaces, slab-edge
-// columns, and the ring around them) is advanced by two ordinary list passes
-// on the edge stream (step_pair in plb_api.cu).  The arithmetic per node and
-// step is the same collide<>() as everywhere else, so the strict build stays
-// bit-identical to the reference.
-constexpr int FUSED_SPAN = 62;
+// A node is deep enough for DEPTH steps if every node within Chebyshev
+// distance DEPTH - 1 is a bulk node (`deep` plane: that distance, capped).
+// Every other node (domain edges, obstacle surfaces, slab-edge columns, and the
+// rings around them) is advanced by DEPTH ordinary list passes on the edge
+// stream (step_fused in plb_api.cu).  The arithmetic per node and step is the
+// same collide<>() as everywhere else, so the strict build stays bit-identical
+// to the reference.
+__host__ __device__ constexpr int fused_span(int depth) { return 64 - 2 * (depth - 1); }
 #ifndef PLB_FUSED_BLOCK
 #define PLB_FUSED_BLOCK 128
 #endif
@@ -328,8 +331,10 @@ constexpr int FUSED_SPAN = 62;
 // Resident CTAs per SM asked of ptxas, per collision model (PLB_FUSED_MINBLOCKS
 // for all, PLB_FUSED_MINBLOCKS_BGK for the reference-ordered BGK kernels, which
 // need more registers than the two-stress-moment MRT).
-__host__ __device__ constexpr int fused_min_blocks(int coll)
+__host__ __device__ constexpr int fused_min_blocks(int coll, int depth)
 {
+    // three steps carry 36 doubles per lane: two CTAs (255 registers)
+    if (depth >= 3) return PLB_FUSED_MINBLOCKS > 2 ? 2 : PLB_FUSED_MINBLOCKS;
 #ifdef PLB_FUSED_MINBLOCKS_BGK
     return coll == 0 ? PLB_FUSED_MINBLOCKS_BGK : PLB_FUSED_MINBLOCKS;
 #else
@@ -389,11 +394,20 @@ __device__ __forceinline__ void fused_stage1(const StepArgs &a, const double fa[
     }
 }
 
-template <int COLL, int FORCING>
-__global__ void __launch_bounds__(PLB_FUSED_BLOCK, fused_min_blocks(COLL))
-k_bulk_fused2(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
-              int64_t x_end, int32_t strips, int32_t rows_per_chunk)
+// Post-collision populations of the two previous rows of one level, already
+// shifted to the lanes that pull them.
+struct FusedCarry {
+    double pa[3], pb[3];   // two rows back: k = 1, 5, 8
+    double na[3], nb[3];   // one row back : k = 1, 5, 8
+    double ca[3], cb[3];   // one row back : k = 0, 2, 4
+};
+
+template <int COLL, int FORCING, int DEPTH>
+__global__ void __launch_bounds__(PLB_FUSED_BLOCK, fused_min_blocks(COLL, DEPTH))
+k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
+             int64_t x_end, int32_t strips, int32_t rows_per_chunk)
 {
+    constexpr int LEVELS = DEPTH - 1;              // hand-overs in registers
     const Layout &L = a.p.L;
     const int lane = threadIdx.x & 31;
     const int64_t warp = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -402,15 +416,21 @@ k_bulk_fused2(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
     const int64_t xs = x_begin + chunk * rows_per_chunk;
     if (xs >= x_end) return;                       // whole warp
     const int64_t xe = (xs + rows_per_chunk < x_end) ? xs + rows_per_chunk : x_end;
-    const int64_t y = int64_t(strip) * FUSED_SPAN - 2 + 2 * lane;
+    const int64_t y = int64_t(strip) * fused_span(DEPTH) - 2 + 2 * lane;
     // the pair lies inside the padded row (y >= -2 is column >= 14)
     const bool in_row = L.y0 + y + 1 < L.pitch;
     const int64_t plane = L.plane, pitch = L.pitch;
+    // After LEVELS hand-overs the strip has lost LEVELS nodes at either end:
+    // this lane still delivers node y / node y + 1 if ...
+    const bool lane_a = 2 * lane >= LEVELS && 2 * lane <= 63 - LEVELS;
+    const bool lane_b = 2 * lane + 1 >= LEVELS && 2 * lane + 1 <= 63 - LEVELS;
 
-    // Rows xs - 1 .. xe go through stage 1 in order (row number i = 0 ..);
-    // from i = 2 on, row x = xs + i - 2 is complete and goes through stage 2.
-    const int n_rows = int(xe - xs) + 2;
-    const double *row0 = a.fin + L.at(xs - 1, y);          // pair of row i = 0
+    // Rows xs - LEVELS .. xe - 1 + LEVELS go through level 0 in order (row
+    // number i = 0 ..); row number i leaves level l (0-based) as the complete
+    // state of row i - 1 one step later, meaningful from i = 2 (l + 1) on; the
+    // row pushed into B in iteration i is x = xs + i - 2 LEVELS.
+    const int n_rows = int(xe - xs) + 2 * LEVELS;
+    const double *row0 = a.fin + L.at(xs - LEVELS, y);     // pair of row i = 0
 #if PLB_FUSED_STAGES >= 2
     constexpr int AHEAD = PLB_FUSED_STAGES - 1;
     __shared__ double2 ring[PLB_FUSED_STAGES][Q][PLB_FUSED_BLOCK];
@@ -425,18 +445,22 @@ k_bulk_fused2(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
     }
 #endif
 
-    // post-collision populations of earlier rows, shifted to their pullers
-    double pa[3] = {0, 0, 0}, pb[3] = {0, 0, 0};   // row x - 1: k = 1, 5, 8
-    double na[3] = {0, 0, 0}, nb[3] = {0, 0, 0};   // row x    : k = 1, 5, 8
-    double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};   // row x    : k = 0, 2, 4
+    FusedCarry carry[LEVELS];
+#pragma unroll
+    for (int l = 0; l < LEVELS; ++l)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            carry[l].pa[j] = carry[l].pb[j] = carry[l].na[j] = carry[l].nb[j] =
+                carry[l].ca[j] = carry[l].cb[j] = 0.0;
 
-    // deep flags of the row that goes through stage 2 in the NEXT iteration:
-    // fetched one iteration ahead, so that the vote below never waits for them
+    // deep flags of the row that is pushed in the NEXT iteration: fetched one
+    // iteration ahead, so that the vote below never waits for them
     uint16_t dd_next = 0;
     for (int i = 0; i < n_rows; ++i) {
         const uint16_t dd = dd_next;
-        if (in_row && i >= 1 && i + 1 < n_rows)
-            dd_next = *reinterpret_cast<const uint16_t *>(deep + L.at(xs + i - 1, y));
+        if (in_row && i + 1 >= 2 * LEVELS && i + 1 < n_rows)
+            dd_next = *reinterpret_cast<const uint16_t *>(
+                deep + L.at(xs + i + 1 - 2 * LEVELS, y));
         double fa[Q], fb[Q];
 #if PLB_FUSED_STAGES >= 2
         {
@@ -468,56 +492,71 @@ k_bulk_fused2(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
             fb[k] = v.y;
         }
 #endif
-        double sa[Q], sb[Q];
-        fused_stage1<COLL, FORCING>(a, fa, fb, sa, sb);
-
-        // time t + 1 populations of row x = xs + i - 2 (meaningful from i = 2)
-        fa[0] = ca[0]; fa[1] = pa[0]; fa[2] = ca[1]; fa[3] = sa[3]; fa[4] = ca[2];
-        fa[5] = pa[1]; fa[6] = sa[6]; fa[7] = sa[7]; fa[8] = pa[2];
-        fb[0] = cb[0]; fb[1] = pb[0]; fb[2] = cb[1]; fb[3] = sb[3]; fb[4] = cb[2];
-        fb[5] = pb[1]; fb[6] = sb[6]; fb[7] = sb[7]; fb[8] = pb[2];
+        bool complete = true;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            pa[j] = na[j];
-            pb[j] = nb[j];
+        for (int l = 0; l < LEVELS; ++l) {
+            if (!complete) break;
+            double sa[Q], sb[Q];
+            fused_stage1<COLL, FORCING>(a, fa, fb, sa, sb);
+            FusedCarry &c = carry[l];
+            // one step later: the populations of the row one back
+            fa[0] = c.ca[0]; fa[1] = c.pa[0]; fa[2] = c.ca[1]; fa[3] = sa[3]; fa[4] = c.ca[2];
+            fa[5] = c.pa[1]; fa[6] = sa[6]; fa[7] = sa[7]; fa[8] = c.pa[2];
+            fb[0] = c.cb[0]; fb[1] = c.pb[0]; fb[2] = c.cb[1]; fb[3] = sb[3]; fb[4] = c.cb[2];
+            fb[5] = c.pb[1]; fb[6] = sb[6]; fb[7] = sb[7]; fb[8] = c.pb[2];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                c.pa[j] = c.na[j];
+                c.pb[j] = c.nb[j];
+            }
+            c.na[0] = sa[1]; c.na[1] = sa[5]; c.na[2] = sa[8];
+            c.nb[0] = sb[1]; c.nb[1] = sb[5]; c.nb[2] = sb[8];
+            c.ca[0] = sa[0]; c.ca[1] = sa[2]; c.ca[2] = sa[4];
+            c.cb[0] = sb[0]; c.cb[1] = sb[2]; c.cb[2] = sb[4];
+            complete = i >= 2 * (l + 1);
         }
-        na[0] = sa[1]; na[1] = sa[5]; na[2] = sa[8];
-        nb[0] = sb[1]; nb[1] = sb[5]; nb[2] = sb[8];
-        ca[0] = sa[0]; ca[1] = sa[2]; ca[2] = sa[4];
-        cb[0] = sb[0]; cb[1] = sb[2]; cb[2] = sb[4];
-        if (i < 2) continue;
+        if (!complete) continue;
 
-        const int64_t idx = L.at(xs + i - 2, y);
-        // a lane delivers node y unless it is lane 0, node y + 1 unless lane 31
-        const bool da = (dd & 0xff) != 0 && lane != 0;
-        const bool db = (dd >> 8) != 0 && lane != 31;
+        const int64_t idx = L.at(xs + i - 2 * LEVELS, y);
+        const bool da = (dd & 0xff) >= LEVELS && lane_a;
+        const bool db = (dd >> 8) >= LEVELS && lane_b;
         if (!__any_sync(0xffffffffu, da || db)) continue;
 
         double ha[Q], hb[Q];
         collide<COLL, FORCING>(a.p, fa, ha);
         collide<COLL, FORCING>(a.p, fb, hb);
 
-        if (__all_sync(0xffffffffu, (da || lane == 0) && (db || lane == 31))) {
-            // all 62 nodes are deep: 128-bit stores, pairs re-aligned by shuffle
+        if (__all_sync(0xffffffffu, (da || !lane_a) && (db || !lane_b))) {
+            // every node the warp can deliver is deep: 128-bit stores, pairs
+            // re-aligned by shuffle (a pair whose other half belongs to a lost
+            // node shrinks to a 64-bit store)
 #pragma unroll
             for (int k = 0; k < Q; ++k) {
                 double *dst = a.fout + k * plane + idx + d_cx[k] * pitch;
+                double lo, hi;
+                bool lo_ok, hi_ok;
                 if (d_cy[k] == 0) {
-                    if (lane == 0) st1(dst + 1, hb[k]);
-                    else if (lane == 31) st1(dst, ha[k]);
-                    else st2(dst, ha[k], hb[k]);
+                    lo = ha[k]; hi = hb[k];
+                    lo_ok = lane_a; hi_ok = lane_b;
                 } else if (d_cy[k] == 1) {
                     // values move to y + 1, y + 2: pair [y, y+1] = (left b, own a)
-                    const double up = __shfl_up_sync(0xffffffffu, hb[k], 1);
-                    if (lane != 0) st2(dst, up, ha[k]);
+                    lo = __shfl_up_sync(0xffffffffu, hb[k], 1);
+                    hi = ha[k];
+                    lo_ok = lane > 0 && 2 * lane - 1 <= 63 - LEVELS && 2 * lane - 1 >= LEVELS;
+                    hi_ok = lane_a;
                 } else {
                     // values move to y - 1, y: pair [y, y+1] = (own b, right a)
-                    const double dn = __shfl_down_sync(0xffffffffu, ha[k], 1);
-                    if (lane != 31) st2(dst, hb[k], dn);
+                    lo = hb[k];
+                    hi = __shfl_down_sync(0xffffffffu, ha[k], 1);
+                    lo_ok = lane_b;
+                    hi_ok = lane < 31 && 2 * lane + 2 >= LEVELS && 2 * lane + 2 <= 63 - LEVELS;
                 }
+                if (lo_ok && hi_ok) st2(dst, lo, hi);
+                else if (lo_ok) st1(dst, lo);
+                else if (hi_ok) st1(dst + 1, hi);
             }
         } else {
-            // strip touches a non-deep node (domain edge, obstacle, its ring)
+            // strip touches a node that is not deep (domain edge, obstacle, ring)
 #pragma unroll
             for (int k = 0; k < Q; ++k) {
                 double *dst = a.fout + k * plane + idx + d_cx[k] * pitch + d_cy[k];
@@ -916,16 +955,18 @@ int launch_bulk(const StepArgs &a, int64_t x_begin, int64_t x_end, int variant,
     return 1;
 }
 
-int fused_strips(const Layout &L)
+int fused_strips(const Layout &L, int depth)
 {
-    return int((L.ny + 1 + FUSED_SPAN - 1) / FUSED_SPAN);
+    // strip j delivers y in [span j + depth - 3, span (j + 1) + depth - 3)
+    const int span = fused_span(depth);
+    return int((L.ny + 3 - depth + span - 1) / span);
 }
 
-template <int C, int F>
+template <int C, int F, int D>
 static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
                       int64_t x_end, int32_t rows_per_chunk, cudaStream_t st)
 {
-    const int32_t strips = fused_strips(a.p.L);
+    const int32_t strips = fused_strips(a.p.L, D);
     const int64_t chunks = (x_end - x_begin + rows_per_chunk - 1) / rows_per_chunk;
     const int64_t warps = chunks * strips;
     constexpr int wpb = PLB_FUSED_BLOCK / 32;
@@ -933,24 +974,28 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
     // the prefetch ring wants shared memory, nothing here wants L1
     static bool carveout_set = false;
     if (!carveout_set) {
-        cudaFuncSetAttribute(k_bulk_fused2<C, F>,
+        cudaFuncSetAttribute(k_bulk_fused<C, F, D>,
                              cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
         carveout_set = true;
     }
 #endif
-    PLB_LAUNCH(COOP, (k_bulk_fused2<C, F>), unsigned((warps + wpb - 1) / wpb),
+    PLB_LAUNCH(COOP, (k_bulk_fused<C, F, D>), unsigned((warps + wpb - 1) / wpb),
                PLB_FUSED_BLOCK, st, a, deep, x_begin, x_end, strips,
                rows_per_chunk);
 }
 
-int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
-                      int64_t x_end, int32_t rows_per_chunk, cudaStream_t stream)
+int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
+                      int64_t x_begin, int64_t x_end, int32_t rows_per_chunk,
+                      cudaStream_t stream)
 {
-    if (x_end <= x_begin) return 0;
+    if (x_end <= x_begin || depth < 2 || depth > 3) return 0;
 #define PLB_CASE(C, F)                                                        \
     if (a.collision == C && a.forcing == F) {                                 \
-        run_fused<C, F>(a, deep, x_begin, x_end, rows_per_chunk, stream);     \
+        if (depth == 2)                                                       \
+            run_fused<C, F, 2>(a, deep, x_begin, x_end, rows_per_chunk, stream); \
+        else                                                                  \
+            run_fused<C, F, 3>(a, deep, x_begin, x_end, rows_per_chunk, stream); \
         return 1;                                                             \
     }
     PLB_CASE(0, 0) PLB_CASE(0, 1) PLB_CASE(0, 2)

@@ -246,8 +246,14 @@ struct LaunchOp : Op {
     {
         g_gridDim = grid;
         g_blockDim = block;
-        for (; next_block < grid.x; ++next_block)
-            if (!run_block(mode, next_block, block, body)) return false;
+        // PLB_EMU_BLOCK_ORDER=reverse runs the blocks last to first: a result
+        // that depends on the order has two writers for one location
+        const char *order = getenv("PLB_EMU_BLOCK_ORDER");
+        const bool reverse = order && order[0] == 'r';
+        for (; next_block < grid.x; ++next_block) {
+            const unsigned b = reverse ? grid.x - 1 - next_block : next_block;
+            if (!run_block(mode, b, block, body)) return false;
+        }
         return true;
     }
 };

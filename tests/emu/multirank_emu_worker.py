@@ -87,9 +87,9 @@ def main():
         try:
             for spec in specs:
                 name, steps, mode, face, *rest = spec.split(":")
+                fuse, depth = mw.fuse_options(rest)
                 status = mw.run_one(comm, name, int(steps), mode == "strict", face,
-                                    tmp, fuse="2" if "fuse2" in rest else
-                                    "0" if "fuse0" in rest else "1")
+                                    tmp, fuse=fuse, depth=depth)
                 if rank == 0:
                     results[spec] = status
         except BaseException as e:       # noqa: BLE001 -- the other ranks would hang

@@ -73,11 +73,24 @@ def global_oracle(sim):
     return orc, st
 
 
-def run_one(comm, name, steps, strict, face, out_dir, fuse="1"):
+def fuse_options(tokens):
+    """Spec suffixes -> (PLB_FUSE, PLB_FUSE_DEPTH): "fuse2" / "fuse3" force two /
+    three steps per pass on any lattice, "fuse0" single steps only."""
+    if "fuse3" in tokens:
+        return "2", "3"
+    if "fuse2" in tokens:
+        return "2", "2"
+    if "fuse0" in tokens:
+        return "0", "2"
+    return "1", "2"
+
+
+def run_one(comm, name, steps, strict, face, out_dir, fuse="1", depth="2"):
     """One decomposed run against the global oracle; returns 0 on parity."""
     rank, world = comm.Get_rank(), comm.Get_size()
     os.environ["PLB_FACE"] = face
-    os.environ["PLB_FUSE"] = fuse        # 2: two steps per pass on any lattice
+    os.environ["PLB_FUSE"] = fuse
+    os.environ["PLB_FUSE_DEPTH"] = depth
     sim = CASES[name]()
     sim.decompose_dict = {"nx": world, "ny": 1}
     solver = Solver(comm, "b200", simulation=sim, strict=strict, verbose=False,
@@ -88,7 +101,10 @@ def run_one(comm, name, steps, strict, face, out_dir, fuse="1"):
     solver.plb.initialize_pop()
     solver.advance(steps, store_moments_last=True)
     solver.plb.sync()
-    pairs = solver.plb.fused_info()["pairs"]
+    finfo = solver.plb.fused_info()
+    pairs = finfo["pairs"] + finfo["triples"]
+    if depth == "3" and finfo["n_deep3"] > 0 and steps > 3 and finfo["triples"] == 0:
+        pairs = 0
     got = solver.fields_to_host()
     shape = solver.state.domain.shape
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"),
@@ -156,9 +172,9 @@ def main():
     for spec in specs:
         name, steps, mode, face, *rest = spec.split(":")
         try:
+            fuse, depth = fuse_options(rest)
             results[spec] = run_one(comm, name, int(steps), mode == "strict",
-                                    face, out_dir,
-                                    fuse="2" if "fuse2" in rest else "1")
+                                    face, out_dir, fuse=fuse, depth=depth)
         except Exception as e:           # noqa: BLE001 -- report, then stop:
             print(f"[multirank] {spec}: {type(e).__name__}: {e}", flush=True)
             results[spec] = 2            # the ranks are no longer in step

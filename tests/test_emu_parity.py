@@ -8,8 +8,8 @@ arithmetic of the -fmad=false build, so BGK paths must equal the reference's
 golden vectors bit for bit.  What is checked here is what needs no hardware:
 indexing, the shuffle-assembled 128-bit store patterns, warp-edge cases, the
 node classification, the list passes and the host-side ordering of the
-single-step path and of the two-steps-per-pass path (k_bulk_fused2 /
-step_pair).  The `-m gpu` tests remain the parity tests proper.
+single-step path and of the two-steps-per-pass path (k_bulk_fused /
+step_fused).  The `-m gpu` tests remain the parity tests proper.
 """
 import os
 import sys
@@ -40,6 +40,8 @@ def emu(emu_lib, monkeypatch):
     loader's explicit override; the product default never points here)."""
     monkeypatch.setenv("PLB_LIB", emu_lib)
     monkeypatch.delenv("PLB_FUSED_ROWS", raising=False)
+    monkeypatch.delenv("PLB_FUSE_DEPTH", raising=False)
+    monkeypatch.delenv("PLB_EMU_BLOCK_ORDER", raising=False)
     monkeypatch.delenv("PLB_KERNEL", raising=False)
     return monkeypatch
 
@@ -144,12 +146,16 @@ WIDE_CASES = {
 }
 
 
-def _run(sim_factory, n_steps, fuse, emu, rows=None, one_by_one=False):
+def _run(sim_factory, n_steps, fuse, emu, rows=None, one_by_one=False, depth=2):
     emu.setenv("PLB_FUSE", fuse)
+    emu.setenv("PLB_FUSE_DEPTH", str(depth))
     if rows is None:
         emu.delenv("PLB_FUSED_ROWS", raising=False)
     else:
         emu.setenv("PLB_FUSED_ROWS", str(rows))
+    # CTAs last to first for the chunked runs: a result that depended on the
+    # order of the CTAs would have two writers for one slot
+    emu.setenv("PLB_EMU_BLOCK_ORDER", "reverse" if rows in (5, 7) else "forward")
     s = make_solver(sim_factory())
     try:
         if one_by_one:
@@ -182,6 +188,47 @@ def test_two_steps_per_pass_equals_two_single_steps(emu, name):
             assert np.array_equal(got[key], want[key]), (name, rows, key)
 
 
+@pytest.mark.parametrize("name", sorted(WIDE_CASES))
+def test_three_steps_per_pass_equals_three_single_steps(emu, name):
+    """PLB_FUSE_DEPTH=3: the same kernel template one level deeper (60 of 64
+    nodes per warp strip, chunks overlap by four rows, three list passes, two
+    scratch lattices); 14 steps = 4 triples + 1 pair."""
+    factory = WIDE_CASES[name]
+    want, _ = _run(factory, 15, "0", emu)
+    for rows, one_by_one in ((None, False), (7, False), (64, True)):
+        got, info = _run(factory, 15, "2", emu, rows=rows, one_by_one=one_by_one,
+                         depth=3)
+        if info["n_deep3"] > 0:
+            assert info["active"] == 3 and info["triples"] == 4 and info["pairs"] == 1, info
+        elif info["n_deep"] > 0:
+            assert info["active"] == 2 and info["pairs"] == 7, info
+        else:
+            assert info["active"] == 0
+        for key in ("density", "velocity", "pop_fluid_new"):
+            assert np.array_equal(got[key], want[key]), (name, rows, key)
+
+
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN_CASES))
+def test_three_steps_per_pass_is_bit_exact_with_reference(golden_dir, emu, name):
+    emu.setenv("PLB_FUSE", "2")
+    emu.setenv("PLB_FUSE_DEPTH", "3")
+    factory, kwargs, record = cases.GOLDEN_CASES[name]
+    data = np.load(os.path.join(golden_dir, name + ".npz"))
+    s = make_solver(factory(**kwargs))
+    try:
+        done = 0
+        for step in record:
+            s.advance(step - done, store_moments_last=True)
+            done = step
+            got = s.fields_to_host()
+            assert np.array_equal(got["density"], data[f"density_{step}"]), step
+            assert np.array_equal(got["velocity"], data[f"velocity_{step}"]), step
+            assert np.array_equal(got["pop_fluid_new"], data[f"pop_{step}"]), step
+        assert s.plb.fused_info()["triples"] > 0
+    finally:
+        s.close()
+
+
 @pytest.mark.parametrize("name", ["poiseuille_70x140_guo2", "cylinder_120x140",
                                   "mrt_poiseuille_70x140_guo2",
                                   "zero_gradient_100x127"])
@@ -212,7 +259,7 @@ def test_default_mode_pairs_only_where_deep_nodes_dominate(emu):
     try:
         assert small.plb.fused_info()["active"] == 0
         info = large.plb.fused_info()
-        assert info["active"] == 1 and info["n_deep"] == 97 * 97
+        assert info["active"] == 2 and info["n_deep"] == 97 * 97
         large.advance(10)
         large.plb.sync()
         assert large.plb.fused_info()["pairs"] == 5

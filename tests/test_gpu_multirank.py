@@ -49,7 +49,11 @@ TWO_SLABS = ([f"{n}:25:strict:p2p" for n in NAMES] +
               "poiseuille:401:strict:nccl:fuse2",
               "wide_channel:41:production:p2p:fuse2",
               "wide_cylinder:40:strict:p2p:fuse2",
-              "wide_channel:40:strict:nccl:fuse2"])
+              "wide_channel:40:strict:nccl:fuse2"] +
+             # three steps per pass (PLB_FUSE_DEPTH=3, opt-in)
+             ["periodic_box:25:strict:p2p:fuse3", "cylinder_cut:26:strict:nccl:fuse3",
+              "wide_channel:41:strict:p2p:fuse3", "wide_cylinder:40:strict:nccl:fuse3",
+              "poiseuille:400:strict:p2p:fuse3"])
 FOUR_SLABS = ([f"{n}:25:strict:p2p" for n in
                ("poiseuille", "cylinder_cut", "periodic_box")] +
               ["periodic_box:25:strict:nccl", "mrt_box:300:production:p2p",
@@ -57,7 +61,8 @@ FOUR_SLABS = ([f"{n}:25:strict:p2p" for n in
                "uneven:40:strict:p2p", "uneven:41:strict:p2p:fuse2",
                "periodic_box:25:strict:p2p:fuse2",
                "wide_channel:60:strict:nccl:fuse2",
-               "wide_cylinder:60:strict:p2p:fuse2"])
+               "wide_cylinder:60:strict:p2p:fuse2",
+               "uneven:41:strict:p2p:fuse3", "wide_cylinder:61:strict:p2p:fuse3"])
 
 
 def _launch(world, specs, port):
