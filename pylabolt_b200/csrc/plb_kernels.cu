@@ -907,7 +907,8 @@ struct BulkScalar {
                     cudaStream_t st)
     {
         const int32_t chunks = int32_t((a.p.L.ny + 255) / 256);
-        PLB_LAUNCH(SIMPLE, (k_bulk_scalar<C, F, S>), unsigned(n_rows * chunks), 256, st, a, x_begin, chunks);
+        PLB_LAUNCH(SIMPLE, (k_bulk_scalar<C, F, S>), unsigned(n_rows * chunks), 256, st, a,
+                   x_begin, chunks);
     }
 };
 
@@ -918,7 +919,8 @@ struct BulkVec2 {
     {
         constexpr int span = 2 * PLB_BLOCK;
         const int32_t chunks = int32_t((a.p.L.ny + span - 1) / span);
-        PLB_LAUNCH(COOP, (k_bulk_vec2<C, F, S>), unsigned(n_rows * chunks), PLB_BLOCK, st, a, x_begin, chunks);
+        PLB_LAUNCH(COOP, (k_bulk_vec2<C, F, S>), unsigned(n_rows * chunks), PLB_BLOCK, st, a,
+                   x_begin, chunks);
     }
 };
 
@@ -928,7 +930,8 @@ struct BulkEdge {
                     cudaStream_t st)
     {
         const int32_t chunks = int32_t((a.p.L.ny + 255) / 256);
-        PLB_LAUNCH(SIMPLE, (k_bulk_edge<C, F, S>), unsigned(n_rows * chunks), 256, st, a, x_begin, chunks);
+        PLB_LAUNCH(SIMPLE, (k_bulk_edge<C, F, S>), unsigned(n_rows * chunks), 256, st, a,
+                   x_begin, chunks);
     }
 };
 
@@ -1035,7 +1038,8 @@ int launch_zero_gradient(double *fout, int64_t plane, const ZgLink *links,
                          int64_t n_links, cudaStream_t stream)
 {
     if (n_links <= 0) return 0;
-    PLB_LAUNCH(SIMPLE, (k_zero_gradient), unsigned((n_links + 127) / 128), 128, stream, fout, plane, links, n_links);
+    PLB_LAUNCH(SIMPLE, (k_zero_gradient), unsigned((n_links + 127) / 128), 128, stream, fout,
+               plane, links, n_links);
     return 1;
 }
 
@@ -1047,7 +1051,9 @@ int launch_face_unpack(const Layout &L, double *fout, int64_t x_col,
                        unsigned long long wait_value, unsigned long long *status,
                        long long spin_budget)
 {
-    PLB_LAUNCH(COOP, (k_face_unpack), unsigned((L.ny + 255) / 256), 256, stream, L, fout, x_col, dirs[0], dirs[1], dirs[2], src, src_stride0, src_stride1, src_stride2, mask, wait_flag, wait_value, status, spin_budget);
+    PLB_LAUNCH(COOP, (k_face_unpack), unsigned((L.ny + 255) / 256), 256, stream, L, fout,
+               x_col, dirs[0], dirs[1], dirs[2], src, src_stride0, src_stride1, src_stride2,
+               mask, wait_flag, wait_value, status, spin_budget);
     return 1;
 }
 
@@ -1055,7 +1061,8 @@ int launch_init_pop(const KParams &p, double *f, const uint8_t *code,
                     const double *rho, const double *ux, const double *uy,
                     cudaStream_t stream)
 {
-    PLB_LAUNCH(SIMPLE, (k_init_pop), unsigned((p.L.plane + 255) / 256), 256, stream, p, f, code, rho, ux, uy);
+    PLB_LAUNCH(SIMPLE, (k_init_pop), unsigned((p.L.plane + 255) / 256), 256, stream, p, f,
+               code, rho, ux, uy);
     return 1;
 }
 
@@ -1064,7 +1071,8 @@ int launch_unpack_rows(const Layout &L, const double *staging, int ncomp,
                        int64_t nrows, cudaStream_t stream)
 {
     const int64_t n = nrows * (L.ny + 2);
-    PLB_LAUNCH(SIMPLE, (k_unpack_rows), unsigned((n + 255) / 256), 256, stream, L, staging, ncomp, planes, plane_stride, row0, nrows);
+    PLB_LAUNCH(SIMPLE, (k_unpack_rows), unsigned((n + 255) / 256), 256, stream, L, staging,
+               ncomp, planes, plane_stride, row0, nrows);
     return 1;
 }
 
@@ -1074,7 +1082,8 @@ int launch_pack_rows(const Layout &L, double *staging, int ncomp,
                      cudaStream_t stream)
 {
     const int64_t n = nrows * (L.ny + 2);
-    PLB_LAUNCH(SIMPLE, (k_pack_rows), unsigned((n + 255) / 256), 256, stream, L, staging, ncomp, planes, plane_stride, row0, nrows, zero_mode);
+    PLB_LAUNCH(SIMPLE, (k_pack_rows), unsigned((n + 255) / 256), 256, stream, L, staging,
+               ncomp, planes, plane_stride, row0, nrows, zero_mode);
     return 1;
 }
 
@@ -1083,7 +1092,8 @@ int launch_pack_inner(const Layout &L, double *staging, int ncomp,
                       int64_t nrows, cudaStream_t stream)
 {
     const int64_t n = nrows * L.ny;
-    PLB_LAUNCH(SIMPLE, (k_pack_inner), unsigned((n + 255) / 256), 256, stream, L, staging, ncomp, planes, plane_stride, x0, nrows);
+    PLB_LAUNCH(SIMPLE, (k_pack_inner), unsigned((n + 255) / 256), 256, stream, L, staging,
+               ncomp, planes, plane_stride, x0, nrows);
     return 1;
 }
 
@@ -1092,7 +1102,8 @@ int launch_residue(const Layout &L, const uint8_t *code, const double *rho,
                    double *ux_old, double *uy_old, double *partials,
                    int n_blocks, double *out6, cudaStream_t stream)
 {
-    PLB_LAUNCH(COOP, (k_residue_partial), n_blocks, RES_THREADS, stream, L, code, rho, ux, uy, rho_old, ux_old, uy_old, partials);
+    PLB_LAUNCH(COOP, (k_residue_partial), n_blocks, RES_THREADS, stream, L, code, rho, ux,
+               uy, rho_old, ux_old, uy_old, partials);
     PLB_LAUNCH(SIMPLE, (k_residue_final), 1, 32, stream, partials, n_blocks, out6);
     return 2;
 }

@@ -76,18 +76,6 @@ def test_fused_equals_single_steps(name, monkeypatch):
         assert rel_err(got[key], want[key]) <= RTOL, key
 
 
-@pytest.mark.parametrize("name", sorted(WIDE_CASES))
-def test_three_steps_per_pass_equals_single_steps(name, monkeypatch):
-    """PLB_FUSE_DEPTH=3 (opt-in): 14 plain steps = 4 triples + 1 pair."""
-    factory = WIDE_CASES[name]
-    want, _ = _fields(factory, 15, "0", True, monkeypatch)
-    got, info = _fields(factory, 15, "2", True, monkeypatch, depth=3)
-    if info["n_deep3"] > 0:
-        assert info["triples"] == 4 and info["pairs"] == 1, info
-    for key in ("density", "velocity", "pop_fluid_new"):
-        assert np.array_equal(got[key], want[key]), key
-
-
 MID_CASES = {
     # many strips / chunks / CTAs: the grid of the fused kernel is > 1 wave
     "channel_mrt_guo2_900x1300": lambda: _mrt(cases.poiseuille(900, 1300)),
@@ -102,10 +90,6 @@ def test_fused_equals_single_steps_mid_size(name, monkeypatch):
     want, _ = _fields(factory, 21, "0", True, monkeypatch)
     got, info = _fields(factory, 21, "1", True, monkeypatch)   # default mode
     assert info["active"] == 2 and info["pairs"] == 10
-    for key in ("density", "velocity", "pop_fluid_new"):
-        assert np.array_equal(got[key], want[key]), key
-    got, info = _fields(factory, 21, "1", True, monkeypatch, depth=3)
-    assert info["active"] == 3 and info["triples"] == 6 and info["pairs"] == 1
     for key in ("density", "velocity", "pop_fluid_new"):
         assert np.array_equal(got[key], want[key]), key
 
