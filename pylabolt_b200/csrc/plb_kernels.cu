@@ -331,10 +331,14 @@ __host__ __device__ constexpr int fused_span(int depth) { return 64 - 2 * (depth
 // Resident CTAs per SM asked of ptxas, per collision model (PLB_FUSED_MINBLOCKS
 // for all, PLB_FUSED_MINBLOCKS_BGK for the reference-ordered BGK kernels, which
 // need more registers than the two-stress-moment MRT).
+#ifndef PLB_FUSED_MINBLOCKS_D3
+#define PLB_FUSED_MINBLOCKS_D3 (256 / PLB_FUSED_BLOCK)
+#endif
 __host__ __device__ constexpr int fused_min_blocks(int coll, int depth)
 {
-    // three steps carry 36 doubles per lane: two CTAs (255 registers)
-    if (depth >= 3) return PLB_FUSED_MINBLOCKS > 2 ? 2 : PLB_FUSED_MINBLOCKS;
+    // three steps carry 36 doubles per lane (198 registers for MRT + Guo):
+    // 256 threads per SM unless told otherwise
+    if (depth >= 3) return PLB_FUSED_MINBLOCKS_D3;
 #ifdef PLB_FUSED_MINBLOCKS_BGK
     return coll == 0 ? PLB_FUSED_MINBLOCKS_BGK : PLB_FUSED_MINBLOCKS;
 #else

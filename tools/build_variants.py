@@ -9,11 +9,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pylabolt_b200 import build  # noqa: E402
 
 VARIANTS = {
-    # two-steps-per-pass kernel: prefetch ring depth, CTA size, occupancy
+    # fused kernel (k_bulk_fused): prefetch ring depth, CTA size, occupancy.
+    # Depth 3 is selected at run time (PLB_FUSE_DEPTH=3); PLB_FUSED_MINBLOCKS
+    # applies to depth 2, depth 3 is capped at two 128-thread CTAs.
     "s0": ["-DPLB_FUSED_STAGES=0"],
-    "s2_mb3": ["-DPLB_FUSED_STAGES=2", "-DPLB_FUSED_MINBLOCKS=3"],
+    "s2_mb4": ["-DPLB_FUSED_STAGES=2", "-DPLB_FUSED_MINBLOCKS=4"],
     "s3_b64_mb6": ["-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=6"],
-    "bgk_mb3": ["-DPLB_FUSED_MINBLOCKS_BGK=3"],
+    "s2_b64_mb6": ["-DPLB_FUSED_STAGES=2", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=6"],
+    "s2_b64_mb5": ["-DPLB_FUSED_STAGES=2", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=5"],
+    "s3_b64_mb5": ["-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=5"],
+    # depth 3: 64-thread CTAs, five per SM (204 registers), ring of 2 / 3
+    "d3_b64_mb5": ["-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=6", "-DPLB_FUSED_MINBLOCKS_D3=5"],
+    "d3_s3_b64_mb5": ["-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=6",
+                      "-DPLB_FUSED_MINBLOCKS_D3=5"],
+    "d3_mb3": ["-DPLB_FUSED_MINBLOCKS_D3=3"],
 }
 
 if __name__ == "__main__":
