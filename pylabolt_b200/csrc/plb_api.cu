@@ -1059,86 +1059,103 @@ int plb_finalize_geometry(plb_handle s)
     // depth-d group advances the nodes with deep >= d - 1 in k_bulk_fused and
     // everything else in d list passes: the last list holds the fluid nodes
     // that are not deep enough, each earlier one adds the deep nodes that
-    // touch the list after it (step_fused).
+    // touch the list after it (step_fused).  Whole-plane work is limited to
+    // two separable 3 x 3 erosions and one scan for bytes != 2, all of which
+    // vectorise; the lists are built from the O(perimeter) candidates.
     if (s->fuse_mode != 0) {
-        std::vector<uint8_t> deep(size_t(L.plane), 0);
-        const int64_t P = L.pitch;
-        auto all9 = [P](const uint8_t *c, int64_t y, uint8_t want) {
-            return c[y] == want && c[y - 1] == want && c[y + 1] == want &&
-                   c[y - P] == want && c[y - P - 1] == want && c[y - P + 1] == want &&
-                   c[y + P] == want && c[y + P - 1] == want && c[y + P + 1] == want;
-        };
-        for (int64_t x = 1; x + 1 < nx; ++x) {
-            const uint8_t *c = code.data() + L.at(x, 0);
-            uint8_t *d = deep.data() + L.at(x, 0);
-            for (int64_t y = 1; y + 1 < ny; ++y) d[y] = all9(c, y, NODE_BULK);
-        }
+        const int64_t P = L.pitch, N = L.plane;
+        std::vector<uint8_t> deep(size_t(N), 0);
         {
-            std::vector<uint8_t> one(deep);
-            for (int64_t x = 2; x + 2 < nx; ++x) {
-                const uint8_t *o = one.data() + L.at(x, 0);
-                uint8_t *d = deep.data() + L.at(x, 0);
-                for (int64_t y = 2; y + 2 < ny; ++y)
-                    if (all9(o, y, 1)) d[y] = 2;
+            std::vector<uint8_t> h(size_t(N), 1), bad(size_t(N), 1);
+            const uint8_t *c = code.data();
+            // level 1: no non-bulk code (BULK = 0) in the 3 x 3 neighbourhood
+            for (int64_t i = 1; i + 1 < N; ++i) h[size_t(i)] = c[i - 1] | c[i] | c[i + 1];
+            for (int64_t i = P; i + P < N; ++i)
+                bad[size_t(i)] = (h[size_t(i - P)] | h[size_t(i)] | h[size_t(i + P)]) != 0;
+            // level 2: no level-1 failure in the 3 x 3 neighbourhood
+            for (int64_t i = 1; i + 1 < N; ++i)
+                h[size_t(i)] = bad[size_t(i - 1)] | bad[size_t(i)] | bad[size_t(i + 1)];
+            for (int64_t i = P; i + P < N; ++i)
+                deep[size_t(i)] = uint8_t(!bad[size_t(i)]) +
+                                  uint8_t((h[size_t(i - P)] | h[size_t(i)] | h[size_t(i + P)]) == 0);
+        }
+        // candidates: interior nodes that are not fully deep (a few rings)
+        std::vector<int64_t> candidates;
+        for (int64_t x = 0; x < nx; ++x) {
+            const uint8_t *d = deep.data() + L.at(x, 0);
+            int64_t y = 0;
+            while (y < ny) {
+                uint64_t w;
+                if (y + 8 <= ny && (memcpy(&w, d + y, 8), w == 0x0202020202020202ull)) {
+                    y += 8;
+                    continue;
+                }
+                if (d[y] != 2) candidates.push_back(L.at(x, y));
+                ++y;
             }
         }
         const int64_t n_fluid = n_bulk + int64_t(link_nodes.size());
-        std::vector<uint8_t> on_list(size_t(L.plane), 0), next(size_t(L.plane), 0);
-        for (int depth = 2; depth <= 3; ++depth) {
+        std::vector<uint8_t> on(size_t(N), 0);
+        const int64_t nb8[8] = {-1, 1, -P, -P - 1, -P + 1, P, P - 1, P + 1};
+        for (int depth = 2; depth <= s->fuse_depth; ++depth) {
             const uint8_t need = uint8_t(depth - 1);
-            int64_t n_deep = 0;
-            // last list: fluid nodes that are not deep enough
-            std::fill(on_list.begin(), on_list.end(), 0);
-            for (int64_t x = 0; x < nx; ++x) {
-                const uint8_t *c = code.data() + L.at(x, 0);
-                const uint8_t *d = deep.data() + L.at(x, 0);
-                uint8_t *o = on_list.data() + L.at(x, 0);
-                for (int64_t y = 0; y < ny; ++y) {
-                    const bool fluid = c[y] == NODE_BULK || c[y] == NODE_LINK;
-                    o[y] = fluid && d[y] < need;
-                    n_deep += fluid && d[y] >= need;
+            // last list: fluid nodes that are not deep enough (sorted by index)
+            std::vector<int64_t> cur;
+            for (int64_t idx : candidates) {
+                const uint8_t c = code[size_t(idx)];
+                if ((c == NODE_BULK || c == NODE_LINK) && deep[size_t(idx)] < need) {
+                    on[size_t(idx)] = 1;
+                    cur.push_back(idx);
                 }
             }
-            std::vector<std::vector<LinkNode>> lists;
+            const int64_t n_deep = n_fluid - int64_t(cur.size());
+            std::vector<std::vector<int64_t>> lists;
             lists.resize(size_t(depth));
-            for (int p = depth - 1; p >= 0; --p) {
-                size_t next_link = 0;
-                for (int64_t x = 0; x < nx; ++x) {
-                    const uint8_t *c = code.data() + L.at(x, 0);
-                    const uint8_t *o = on_list.data() + L.at(x, 0);
-                    for (int64_t y = 0; y < ny; ++y) {
-                        if (c[y] == NODE_LINK) {
-                            const LinkNode &ln = link_nodes[next_link++];   // same (x, y) order
-                            lists[size_t(p)].push_back(ln);
-                        } else if (o[y]) {
-                            lists[size_t(p)].push_back(LinkNode{int32_t(x), int32_t(y), 0});
+            lists[size_t(depth - 1)] = cur;
+            for (int p = depth - 2; p >= 0; --p) {
+                // the list before: add the deep nodes next to this one (bulk
+                // nodes with bulk neighbours, so every neighbour index is valid)
+                std::vector<int64_t> add;
+                for (int64_t idx : cur)
+                    for (int64_t off : nb8) {
+                        const int64_t n = idx + off;
+                        if (!on[size_t(n)] && deep[size_t(n)] >= need) {
+                            on[size_t(n)] = 1;
+                            add.push_back(n);
                         }
                     }
-                }
-                if (p == 0) break;
-                // the list before: add the deep nodes next to this one (they
-                // are bulk nodes with bulk neighbours, so x, y are interior)
-                next = on_list;
-                for (int64_t x = 1; x + 1 < nx; ++x) {
-                    const uint8_t *o = on_list.data() + L.at(x, 0);
-                    const uint8_t *d = deep.data() + L.at(x, 0);
-                    uint8_t *nn = next.data() + L.at(x, 0);
-                    for (int64_t y = 1; y + 1 < ny; ++y)
-                        if (!o[y] && d[y] >= need &&
-                            (o[y - 1] | o[y + 1] | o[y - P] | o[y - P - 1] | o[y - P + 1] |
-                             o[y + P] | o[y + P - 1] | o[y + P + 1]))
-                            nn[y] = 1;
-                }
-                on_list.swap(next);
+                std::sort(add.begin(), add.end());
+                std::vector<int64_t> merged(cur.size() + add.size());
+                std::merge(cur.begin(), cur.end(), add.begin(), add.end(), merged.begin());
+                cur.swap(merged);
+                lists[size_t(p)] = cur;
             }
+            for (int64_t idx : lists[0]) on[size_t(idx)] = 0;   // clean for the next depth
             s->n_deep[depth - 2] = n_deep;
             const bool ok = n_deep > 0 &&
                             (s->fuse_mode == 2 ||
                              (int64_t(lists[0].size()) * 8 <= n_fluid && n_fluid >= 4096));
-            if (!ok || depth > s->fuse_depth) continue;
+            if (!ok) continue;
             s->fused_depth_ok = depth;
             for (int p = 0; p < depth; ++p) {
-                const std::vector<LinkNode> &l = lists[size_t(p)];
+                // index -> record; link nodes (all on every list) keep their codes
+                std::vector<LinkNode> l;
+                l.reserve(lists[size_t(p)].size());
+                size_t next_link = 0;
+                for (int64_t idx : lists[size_t(p)]) {
+                    const int64_t x = idx / P - 1, y = idx % P - L.y0;
+                    if (code[size_t(idx)] == NODE_LINK) {
+                        while (next_link < link_nodes.size() &&
+                               (link_nodes[next_link].x != x || link_nodes[next_link].y != y))
+                            ++next_link;
+                        if (next_link == link_nodes.size())
+                            return fail(PLB_ERR_STATE, "internal: link node (%lld, %lld) "
+                                        "missing from the link list", (long long)x, (long long)y);
+                        l.push_back(link_nodes[next_link++]);
+                    } else {
+                        l.push_back(LinkNode{int32_t(x), int32_t(y), 0});
+                    }
+                }
                 s->n_lists[depth - 2][p] = int64_t(l.size());
                 CUDA_TRY(cudaMalloc(&s->lists_dev[depth - 2][p],
                                     std::max<size_t>(1, l.size()) * sizeof(LinkNode)));

@@ -861,7 +861,7 @@ k_residue_partial(Layout L, const uint8_t *__restrict__ code,
     for (int j = 0; j < 6; ++j) sh[j][threadIdx.x] = acc[j];
     __syncthreads();
     for (int s = RES_THREADS / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s)
+        if (int(threadIdx.x) < s)
             for (int j = 0; j < 6; ++j)
                 sh[j][threadIdx.x] += sh[j][threadIdx.x + s];
         __syncthreads();
