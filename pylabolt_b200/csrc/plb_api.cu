@@ -612,8 +612,11 @@ int step_fused(plb_solver *s, int depth)
             }
         CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used], s->stream));
     }
-    s->launches += launch_bulk_fused(a, s->deep_dev, depth, 0, L.nx, s->fused_rows,
-                                     s->stream);
+    // level 0 reads `depth - 1` rows either side of the rows it delivers and
+    // the lattice has one ghost row: columns closer than depth - 2 to the slab
+    // edge are left out (they cannot be deep enough anyway)
+    s->launches += launch_bulk_fused(a, s->deep_dev, depth, depth - 2, L.nx - (depth - 2),
+                                     s->fused_rows, s->stream);
     if (prof) {
         CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used + 1], s->stream));
         s->prof_used += 2;

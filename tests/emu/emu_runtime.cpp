@@ -17,11 +17,13 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <sys/mman.h>
 #include <ucontext.h>
 #include <vector>
 
@@ -70,6 +72,7 @@ namespace {
 
 std::vector<plb_emu_stream *> g_streams;
 unsigned long long g_seq = 0;
+std::map<char *, std::pair<char *, size_t>> g_allocs;   // pointer -> (mapping, bytes)
 
 // Executes queue heads until nothing moves.  Caller holds the lock.
 bool pump()
@@ -365,13 +368,31 @@ cudaError_t cudaDeviceGetPCIBusId(char *buf, int len, int)
     snprintf(buf, size_t(len), "0000:00:00.0");
     return cudaSuccess;
 }
+// "Device" allocations sit between two inaccessible guard pages, flush against
+// the upper one (PLB_EMU_GUARD=lo: against the lower one), so that a kernel
+// that reads or writes past an end of a buffer dies on the spot instead of
+// quietly using a neighbouring allocation.  Contents start as a 0xA5 pattern:
+// reading memory nobody wrote shows up as a wild value, like on the device.
 cudaError_t plb_emu_malloc(void **p, size_t n)
 {
-    // uninitialised on purpose (0xA5 pattern): reading memory nobody wrote
-    // shows up as a wild value, like on the device
-    *p = malloc(n ? n : 1);
-    if (!*p) return cudaErrorMemoryAllocation;
-    memset(*p, 0xA5, n);
+    const size_t page = 4096;
+    const size_t body = (std::max<size_t>(n, 1) + page - 1) / page * page;
+    const size_t total = body + 2 * page;
+    char *base = static_cast<char *>(mmap(nullptr, total, PROT_READ | PROT_WRITE,
+                                          MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+    if (base == MAP_FAILED) return cudaErrorMemoryAllocation;
+    mprotect(base, page, PROT_NONE);
+    mprotect(base + page + body, page, PROT_NONE);
+    const char *mode = getenv("PLB_EMU_GUARD");
+    char *ptr = base + page;
+    if (!(mode && mode[0] == 'l'))
+        ptr += body - (std::max<size_t>(n, 1) + 15) / 16 * 16;   // 16-byte aligned end
+    memset(ptr, 0xA5, n);
+    {
+        Lock lk(g_mu);
+        plb_emu::g_allocs[ptr] = {base, total};
+    }
+    *p = ptr;
     return cudaSuccess;
 }
 cudaError_t plb_emu_host_alloc(void **p, size_t n)
@@ -381,11 +402,13 @@ cudaError_t plb_emu_host_alloc(void **p, size_t n)
 }
 cudaError_t cudaFree(void *p)
 {
-    {
-        Lock lk(g_mu);
-        plb_emu::pump();
-    }
-    free(p);
+    if (!p) return cudaSuccess;
+    Lock lk(g_mu);
+    plb_emu::pump();
+    auto it = plb_emu::g_allocs.find(static_cast<char *>(p));
+    if (it == plb_emu::g_allocs.end()) plb_emu::die("cudaFree of a pointer cudaMalloc did not return");
+    munmap(it->second.first, it->second.second);
+    plb_emu::g_allocs.erase(it);
     return cudaSuccess;
 }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
