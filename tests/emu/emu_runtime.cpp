@@ -140,8 +140,72 @@ struct Barrier {
     int count = 0;
     unsigned gen = 0;
 };
+
+// Fiber switch.  swapcontext() makes two signal-mask system calls per switch,
+// which dominates a run that switches at every warp shuffle; on x86-64 a
+// fiber is therefore just a saved stack pointer (callee-saved registers,
+// MXCSR and the x87 control word live on its stack).
+#if defined(__x86_64__)
+struct Context {
+    void *sp = nullptr;
+};
+extern "C" void plb_emu_switch(Context *from, Context *to);
+asm(R"(
+    .text
+    .globl plb_emu_switch
+    .type plb_emu_switch,@function
+plb_emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    subq $8, %rsp
+    stmxcsr (%rsp)
+    fnstcw 4(%rsp)
+    movq %rsp, (%rdi)
+    movq (%rsi), %rsp
+    ldmxcsr (%rsp)
+    fldcw 4(%rsp)
+    addq $8, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size plb_emu_switch,.-plb_emu_switch
+)");
+void context_init(Context &c, Context &, char *stack, size_t bytes, void (*entry)())
+{
+    uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + bytes) & ~uintptr_t(15);
+    uint64_t *sp = reinterpret_cast<uint64_t *>(top);
+    *--sp = 0;                                       // return address of entry(): never used
+    *--sp = reinterpret_cast<uint64_t>(entry);       // "return" of the first switch
+    for (int i = 0; i < 6; ++i) *--sp = 0;           // rbp rbx r12 r13 r14 r15
+    *--sp = 0x0000037F00001F80ull;                   // MXCSR | x87 control word << 32
+    c.sp = sp;
+}
+void context_switch(Context &from, Context &to) { plb_emu_switch(&from, &to); }
+#else
+struct Context {
+    ucontext_t uc;
+};
+void context_init(Context &c, Context &back, char *stack, size_t bytes, void (*entry)())
+{
+    getcontext(&c.uc);
+    c.uc.uc_stack.ss_sp = stack;
+    c.uc.uc_stack.ss_size = bytes;
+    c.uc.uc_link = &back.uc;
+    makecontext(&c.uc, entry, 0);
+}
+void context_switch(Context &from, Context &to) { swapcontext(&from.uc, &to.uc); }
+#endif
+
 struct Fiber {
-    ucontext_t ctx;
+    Context ctx;
     char *stack = nullptr;
     bool done = true;
 };
@@ -153,14 +217,14 @@ Barrier g_block_barrier, g_warp_barrier[MAX_THREADS / 32];
 uint64_t g_slot[MAX_THREADS];
 bool g_pred[MAX_THREADS];
 Fiber g_fiber[MAX_THREADS];
-ucontext_t g_sched;
+Context g_sched;
 const std::function<void()> *g_body = nullptr;
 long long g_idle = 0, g_ticks = 0;
 
 void yield()
 {
     if (++g_idle > 50000000LL) die("dead lock: fibers wait at a barrier that cannot complete");
-    swapcontext(&g_fiber[g_cur].ctx, &g_sched);
+    context_switch(g_fiber[g_cur].ctx, g_sched);
 }
 
 void wait(Barrier &b, const int &alive)
@@ -186,7 +250,8 @@ void trampoline()
     --g_alive_block;
     --g_alive_warp[me / 32];
     g_idle = 0;
-    // returning switches to uc_link = the scheduler
+    context_switch(g_fiber[me].ctx, g_sched);        // for good
+    die("a finished fiber was resumed");
 }
 
 void need_coop(const char *what)
@@ -220,12 +285,8 @@ bool run_block(int mode, unsigned b, dim3 block, const std::function<void()> &bo
     for (int t = 0; t < g_n; ++t) {
         Fiber &f = g_fiber[t];
         if (!f.stack) f.stack = static_cast<char *>(malloc(STACK_BYTES));
-        getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = f.stack;
-        f.ctx.uc_stack.ss_size = STACK_BYTES;
-        f.ctx.uc_link = &g_sched;
+        context_init(f.ctx, g_sched, f.stack, STACK_BYTES, trampoline);
         f.done = false;
-        makecontext(&f.ctx, trampoline, 0);
     }
     g_idle = 0;
     while (g_alive_block > 0 && !g_blocked) {
@@ -233,7 +294,7 @@ bool run_block(int mode, unsigned b, dim3 block, const std::function<void()> &bo
             if (g_fiber[t].done) continue;
             g_cur = t;
             g_threadIdx = uint3{unsigned(t), 0, 0};
-            swapcontext(&g_sched, &g_fiber[t].ctx);
+            context_switch(g_sched, g_fiber[t].ctx);
         }
     }
     g_coop = false;
@@ -335,7 +396,7 @@ void sleep_hook()
 {
     need_coop("__nanosleep (a polling kernel) in a kernel launched in SIMPLE mode");
     g_blocked = true;
-    swapcontext(&g_fiber[g_cur].ctx, &g_sched);
+    context_switch(g_fiber[g_cur].ctx, g_sched);
     die("an abandoned fiber was resumed");
 }
 
