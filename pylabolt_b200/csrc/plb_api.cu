@@ -176,6 +176,7 @@ struct plb_solver {
     int64_t n_lists[2][3] = {};
     int64_t n_deep[2] = {0, 0};          // nodes the depth-2 / depth-3 kernel advances
     int32_t fused_rows = 32;             // rows a warp marches over (PLB_FUSED_ROWS)
+    unsigned *work_counter = nullptr;    // PLB_FUSED_DYNAMIC=1: persistent grid, work queue
     int64_t pending = 0;                 // plain steps held back for grouping
     int64_t groups_done[2] = {0, 0};
 
@@ -616,7 +617,7 @@ int step_fused(plb_solver *s, int depth)
     // the lattice has one ghost row: columns closer than depth - 2 to the slab
     // edge are left out (they cannot be deep enough anyway)
     s->launches += launch_bulk_fused(a, s->deep_dev, depth, depth - 2, L.nx - (depth - 2),
-                                     s->fused_rows, s->stream);
+                                     s->fused_rows, s->work_counter, s->stream);
     if (prof) {
         CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used + 1], s->stream));
         s->prof_used += 2;
@@ -898,6 +899,7 @@ void plb_destroy(plb_handle s)
     for (int i = 0; i < 2; ++i) cudaFree(s->f[i]);
     for (int m = 0; m < 2; ++m) cudaFree(s->f_mid[m]);
     cudaFree(s->deep_dev);
+    cudaFree(s->work_counter);
     for (int d = 0; d < 2; ++d)
         for (int p = 0; p < 3; ++p) cudaFree(s->lists_dev[d][p]);
     cudaFree(s->mom);
@@ -1167,6 +1169,8 @@ int plb_finalize_geometry(plb_handle s)
             }
         }
         if (s->fused_depth_ok >= 2) {
+            if (const char *v = getenv("PLB_FUSED_DYNAMIC"))
+                if (atoi(v) != 0) CUDA_TRY(cudaMalloc(&s->work_counter, 256));
             CUDA_TRY(cudaMalloc(&s->deep_dev, deep.size()));
             CUDA_TRY(cudaMemcpy(s->deep_dev, deep.data(), deep.size(), cudaMemcpyHostToDevice));
             if (const char *v = getenv("PLB_FUSED_ROWS")) {

@@ -115,9 +115,11 @@ int launch_bulk(const StepArgs &a, int64_t x_begin, int64_t x_end, int variant,
 // whose deep[] value is >= depth - 1 (fin = time t, fout = time t + depth);
 // deep[] is one byte per node: the Chebyshev distance up to which all
 // neighbours are bulk nodes, capped at 2.
+// work_counter: null = one work item per warp; else a device word (zeroed by
+// the launcher) from which the warps of a persistent grid draw their items.
 int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
                       int64_t x_begin, int64_t x_end, int32_t rows_per_chunk,
-                      cudaStream_t stream);
+                      unsigned *work_counter, cudaStream_t stream);
 int fused_strips(const Layout &L, int depth);
 // One slab-edge column with the face redirection of StepArgs::face_lo/hi.
 int launch_bulk_edge(const StepArgs &a, int64_t x_begin, int64_t x_end,

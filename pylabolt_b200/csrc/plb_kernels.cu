@@ -18,6 +18,8 @@
 //   k_zero_gradient             : thin pass for zero_gradient elements
 //   k_face_unpack               : slab-face / periodic-x delivery of the
 //                                 three populations that cross a face
+#include <algorithm>
+
 #include "plb_collide.cuh"
 
 // Every kernel launch goes through PLB_LAUNCH.  MODE documents (and, in the
@@ -409,165 +411,180 @@ struct FusedCarry {
 template <int COLL, int FORCING, int DEPTH>
 __global__ void __launch_bounds__(PLB_FUSED_BLOCK, fused_min_blocks(COLL, DEPTH))
 k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
-             int64_t x_end, int32_t strips, int32_t rows_per_chunk)
+             int64_t x_end, int32_t strips, int32_t rows_per_chunk,
+             unsigned *work_counter)
 {
     constexpr int LEVELS = DEPTH - 1;              // hand-overs in registers
     const Layout &L = a.p.L;
     const int lane = threadIdx.x & 31;
-    const int64_t warp = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t chunk = warp / strips;
-    const int32_t strip = int32_t(warp - chunk * strips);
-    const int64_t xs = x_begin + chunk * rows_per_chunk;
-    if (xs >= x_end) return;                       // whole warp
-    const int64_t xe = (xs + rows_per_chunk < x_end) ? xs + rows_per_chunk : x_end;
-    const int64_t y = int64_t(strip) * fused_span(DEPTH) - 2 + 2 * lane;
-    // the pair lies inside the padded row (y >= -2 is column >= 14)
-    const bool in_row = L.y0 + y + 1 < L.pitch;
-    const int64_t plane = L.plane, pitch = L.pitch;
-    // After LEVELS hand-overs the strip has lost LEVELS nodes at either end:
-    // this lane still delivers node y / node y + 1 if ...
-    const bool lane_a = 2 * lane >= LEVELS && 2 * lane <= 63 - LEVELS;
-    const bool lane_b = 2 * lane + 1 >= LEVELS && 2 * lane + 1 <= 63 - LEVELS;
-
-    // Rows xs - LEVELS .. xe - 1 + LEVELS go through level 0 in order (row
-    // number i = 0 ..); row number i leaves level l (0-based) as the complete
-    // state of row i - 1 one step later, meaningful from i = 2 (l + 1) on; the
-    // row pushed into B in iteration i is x = xs + i - 2 LEVELS.
-    const int n_rows = int(xe - xs) + 2 * LEVELS;
-    const double *row0 = a.fin + L.at(xs - LEVELS, y);     // pair of row i = 0
 #if PLB_FUSED_STAGES >= 2
-    constexpr int AHEAD = PLB_FUSED_STAGES - 1;
     __shared__ double2 ring[PLB_FUSED_STAGES][Q][PLB_FUSED_BLOCK];
-#pragma unroll
-    for (int i = 0; i < AHEAD; ++i) {
-        if (in_row && i < n_rows) {
-#pragma unroll
-            for (int k = 0; k < Q; ++k)
-                cp_async16(&ring[i][k][threadIdx.x], row0 + k * plane + i * pitch);
-        }
-        cp_async_commit();
-    }
 #endif
+    // One work item = one chunk of rows of one strip.  Statically a warp takes
+    // the item of its own number; with a work counter (PLB_FUSED_DYNAMIC=1,
+    // persistent grid) warps draw items until none is left, so that no SM
+    // idles while the last wave of a static assignment drains.
+    int64_t warp = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (;;) {
+        if (work_counter) {
+            unsigned item = 0;
+            if (lane == 0) item = atomicAdd(work_counter, 1u);
+            warp = __shfl_sync(0xffffffffu, item, 0);
+        }
+        const int64_t chunk = warp / strips;
+        const int32_t strip = int32_t(warp - chunk * strips);
+        const int64_t xs = x_begin + chunk * rows_per_chunk;
+        if (xs >= x_end) return;                       // whole warp
+        const int64_t xe = (xs + rows_per_chunk < x_end) ? xs + rows_per_chunk : x_end;
+        const int64_t y = int64_t(strip) * fused_span(DEPTH) - 2 + 2 * lane;
+        // the pair lies inside the padded row (y >= -2 is column >= 14)
+        const bool in_row = L.y0 + y + 1 < L.pitch;
+        const int64_t plane = L.plane, pitch = L.pitch;
+        // After LEVELS hand-overs the strip has lost LEVELS nodes at either end:
+        // this lane still delivers node y / node y + 1 if ...
+        const bool lane_a = 2 * lane >= LEVELS && 2 * lane <= 63 - LEVELS;
+        const bool lane_b = 2 * lane + 1 >= LEVELS && 2 * lane + 1 <= 63 - LEVELS;
 
-    FusedCarry carry[LEVELS];
-#pragma unroll
-    for (int l = 0; l < LEVELS; ++l)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            carry[l].pa[j] = carry[l].pb[j] = carry[l].na[j] = carry[l].nb[j] =
-                carry[l].ca[j] = carry[l].cb[j] = 0.0;
-
-    // deep flags of the row that is pushed in the NEXT iteration: fetched one
-    // iteration ahead, so that the vote below never waits for them
-    uint16_t dd_next = 0;
-    for (int i = 0; i < n_rows; ++i) {
-        const uint16_t dd = dd_next;
-        if (in_row && i + 1 >= 2 * LEVELS && i + 1 < n_rows)
-            dd_next = *reinterpret_cast<const uint16_t *>(
-                deep + L.at(xs + i + 1 - 2 * LEVELS, y));
-        double fa[Q], fb[Q];
+        // Rows xs - LEVELS .. xe - 1 + LEVELS go through level 0 in order (row
+        // number i = 0 ..); row number i leaves level l (0-based) as the complete
+        // state of row i - 1 one step later, meaningful from i = 2 (l + 1) on; the
+        // row pushed into B in iteration i is x = xs + i - 2 LEVELS.
+        const int n_rows = int(xe - xs) + 2 * LEVELS;
+        const double *row0 = a.fin + L.at(xs - LEVELS, y);     // pair of row i = 0
 #if PLB_FUSED_STAGES >= 2
-        {
-            // refill the slot that was read in the previous iteration
-            const int j = i + AHEAD;
-            if (in_row && j < n_rows) {
+        constexpr int AHEAD = PLB_FUSED_STAGES - 1;
+#pragma unroll
+        for (int i = 0; i < AHEAD; ++i) {
+            if (in_row && i < n_rows) {
 #pragma unroll
                 for (int k = 0; k < Q; ++k)
-                    cp_async16(&ring[j % PLB_FUSED_STAGES][k][threadIdx.x],
-                               row0 + k * plane + j * pitch);
+                    cp_async16(&ring[i][k][threadIdx.x], row0 + k * plane + i * pitch);
             }
             cp_async_commit();
-            cp_async_wait<AHEAD>();                 // row i has landed
-            const int slot = i % PLB_FUSED_STAGES;
+        }
+#endif
+
+        FusedCarry carry[LEVELS];
+#pragma unroll
+        for (int l = 0; l < LEVELS; ++l)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                carry[l].pa[j] = carry[l].pb[j] = carry[l].na[j] = carry[l].nb[j] =
+                    carry[l].ca[j] = carry[l].cb[j] = 0.0;
+
+        // deep flags of the row that is pushed in the NEXT iteration: fetched one
+        // iteration ahead, so that the vote below never waits for them
+        uint16_t dd_next = 0;
+        for (int i = 0; i < n_rows; ++i) {
+            const uint16_t dd = dd_next;
+            if (in_row && i + 1 >= 2 * LEVELS && i + 1 < n_rows)
+                dd_next = *reinterpret_cast<const uint16_t *>(
+                    deep + L.at(xs + i + 1 - 2 * LEVELS, y));
+            double fa[Q], fb[Q];
+#if PLB_FUSED_STAGES >= 2
+            {
+                // refill the slot that was read in the previous iteration
+                const int j = i + AHEAD;
+                if (in_row && j < n_rows) {
+#pragma unroll
+                    for (int k = 0; k < Q; ++k)
+                        cp_async16(&ring[j % PLB_FUSED_STAGES][k][threadIdx.x],
+                                   row0 + k * plane + j * pitch);
+                }
+                cp_async_commit();
+                cp_async_wait<AHEAD>();                 // row i has landed
+                const int slot = i % PLB_FUSED_STAGES;
+#pragma unroll
+                for (int k = 0; k < Q; ++k) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (in_row) v = ring[slot][k][threadIdx.x];
+                    fa[k] = v.x;
+                    fb[k] = v.y;
+                }
+            }
+#else
 #pragma unroll
             for (int k = 0; k < Q; ++k) {
                 double2 v = make_double2(0.0, 0.0);
-                if (in_row) v = ring[slot][k][threadIdx.x];
+                if (in_row) v = ld2(row0 + k * plane + i * pitch);
                 fa[k] = v.x;
                 fb[k] = v.y;
             }
-        }
-#else
-#pragma unroll
-        for (int k = 0; k < Q; ++k) {
-            double2 v = make_double2(0.0, 0.0);
-            if (in_row) v = ld2(row0 + k * plane + i * pitch);
-            fa[k] = v.x;
-            fb[k] = v.y;
-        }
 #endif
-        bool complete = true;
+            bool complete = true;
 #pragma unroll
-        for (int l = 0; l < LEVELS; ++l) {
-            if (!complete) break;
-            double sa[Q], sb[Q];
-            fused_stage1<COLL, FORCING>(a, fa, fb, sa, sb);
-            FusedCarry &c = carry[l];
-            // one step later: the populations of the row one back
-            fa[0] = c.ca[0]; fa[1] = c.pa[0]; fa[2] = c.ca[1]; fa[3] = sa[3]; fa[4] = c.ca[2];
-            fa[5] = c.pa[1]; fa[6] = sa[6]; fa[7] = sa[7]; fa[8] = c.pa[2];
-            fb[0] = c.cb[0]; fb[1] = c.pb[0]; fb[2] = c.cb[1]; fb[3] = sb[3]; fb[4] = c.cb[2];
-            fb[5] = c.pb[1]; fb[6] = sb[6]; fb[7] = sb[7]; fb[8] = c.pb[2];
+            for (int l = 0; l < LEVELS; ++l) {
+                if (!complete) break;
+                double sa[Q], sb[Q];
+                fused_stage1<COLL, FORCING>(a, fa, fb, sa, sb);
+                FusedCarry &c = carry[l];
+                // one step later: the populations of the row one back
+                fa[0] = c.ca[0]; fa[1] = c.pa[0]; fa[2] = c.ca[1]; fa[3] = sa[3]; fa[4] = c.ca[2];
+                fa[5] = c.pa[1]; fa[6] = sa[6]; fa[7] = sa[7]; fa[8] = c.pa[2];
+                fb[0] = c.cb[0]; fb[1] = c.pb[0]; fb[2] = c.cb[1]; fb[3] = sb[3]; fb[4] = c.cb[2];
+                fb[5] = c.pb[1]; fb[6] = sb[6]; fb[7] = sb[7]; fb[8] = c.pb[2];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                c.pa[j] = c.na[j];
-                c.pb[j] = c.nb[j];
-            }
-            c.na[0] = sa[1]; c.na[1] = sa[5]; c.na[2] = sa[8];
-            c.nb[0] = sb[1]; c.nb[1] = sb[5]; c.nb[2] = sb[8];
-            c.ca[0] = sa[0]; c.ca[1] = sa[2]; c.ca[2] = sa[4];
-            c.cb[0] = sb[0]; c.cb[1] = sb[2]; c.cb[2] = sb[4];
-            complete = i >= 2 * (l + 1);
-        }
-        if (!complete) continue;
-
-        const int64_t idx = L.at(xs + i - 2 * LEVELS, y);
-        const bool da = (dd & 0xff) >= LEVELS && lane_a;
-        const bool db = (dd >> 8) >= LEVELS && lane_b;
-        if (!__any_sync(0xffffffffu, da || db)) continue;
-
-        double ha[Q], hb[Q];
-        collide<COLL, FORCING>(a.p, fa, ha);
-        collide<COLL, FORCING>(a.p, fb, hb);
-
-        if (__all_sync(0xffffffffu, (da || !lane_a) && (db || !lane_b))) {
-            // every node the warp can deliver is deep: 128-bit stores, pairs
-            // re-aligned by shuffle (a pair whose other half belongs to a lost
-            // node shrinks to a 64-bit store)
-#pragma unroll
-            for (int k = 0; k < Q; ++k) {
-                double *dst = a.fout + k * plane + idx + d_cx[k] * pitch;
-                double lo, hi;
-                bool lo_ok, hi_ok;
-                if (d_cy[k] == 0) {
-                    lo = ha[k]; hi = hb[k];
-                    lo_ok = lane_a; hi_ok = lane_b;
-                } else if (d_cy[k] == 1) {
-                    // values move to y + 1, y + 2: pair [y, y+1] = (left b, own a)
-                    lo = __shfl_up_sync(0xffffffffu, hb[k], 1);
-                    hi = ha[k];
-                    lo_ok = lane > 0 && 2 * lane - 1 <= 63 - LEVELS && 2 * lane - 1 >= LEVELS;
-                    hi_ok = lane_a;
-                } else {
-                    // values move to y - 1, y: pair [y, y+1] = (own b, right a)
-                    lo = hb[k];
-                    hi = __shfl_down_sync(0xffffffffu, ha[k], 1);
-                    lo_ok = lane_b;
-                    hi_ok = lane < 31 && 2 * lane + 2 >= LEVELS && 2 * lane + 2 <= 63 - LEVELS;
+                for (int j = 0; j < 3; ++j) {
+                    c.pa[j] = c.na[j];
+                    c.pb[j] = c.nb[j];
                 }
-                if (lo_ok && hi_ok) st2(dst, lo, hi);
-                else if (lo_ok) st1(dst, lo);
-                else if (hi_ok) st1(dst + 1, hi);
+                c.na[0] = sa[1]; c.na[1] = sa[5]; c.na[2] = sa[8];
+                c.nb[0] = sb[1]; c.nb[1] = sb[5]; c.nb[2] = sb[8];
+                c.ca[0] = sa[0]; c.ca[1] = sa[2]; c.ca[2] = sa[4];
+                c.cb[0] = sb[0]; c.cb[1] = sb[2]; c.cb[2] = sb[4];
+                complete = i >= 2 * (l + 1);
             }
-        } else {
-            // strip touches a node that is not deep (domain edge, obstacle, ring)
+            if (!complete) continue;
+
+            const int64_t idx = L.at(xs + i - 2 * LEVELS, y);
+            const bool da = (dd & 0xff) >= LEVELS && lane_a;
+            const bool db = (dd >> 8) >= LEVELS && lane_b;
+            if (!__any_sync(0xffffffffu, da || db)) continue;
+
+            double ha[Q], hb[Q];
+            collide<COLL, FORCING>(a.p, fa, ha);
+            collide<COLL, FORCING>(a.p, fb, hb);
+
+            if (__all_sync(0xffffffffu, (da || !lane_a) && (db || !lane_b))) {
+                // every node the warp can deliver is deep: 128-bit stores, pairs
+                // re-aligned by shuffle (a pair whose other half belongs to a lost
+                // node shrinks to a 64-bit store)
 #pragma unroll
-            for (int k = 0; k < Q; ++k) {
-                double *dst = a.fout + k * plane + idx + d_cx[k] * pitch + d_cy[k];
-                if (da) st1(dst, ha[k]);
-                if (db) st1(dst + 1, hb[k]);
+                for (int k = 0; k < Q; ++k) {
+                    double *dst = a.fout + k * plane + idx + d_cx[k] * pitch;
+                    double lo, hi;
+                    bool lo_ok, hi_ok;
+                    if (d_cy[k] == 0) {
+                        lo = ha[k]; hi = hb[k];
+                        lo_ok = lane_a; hi_ok = lane_b;
+                    } else if (d_cy[k] == 1) {
+                        // values move to y + 1, y + 2: pair [y, y+1] = (left b, own a)
+                        lo = __shfl_up_sync(0xffffffffu, hb[k], 1);
+                        hi = ha[k];
+                        lo_ok = lane > 0 && 2 * lane - 1 <= 63 - LEVELS && 2 * lane - 1 >= LEVELS;
+                        hi_ok = lane_a;
+                    } else {
+                        // values move to y - 1, y: pair [y, y+1] = (own b, right a)
+                        lo = hb[k];
+                        hi = __shfl_down_sync(0xffffffffu, ha[k], 1);
+                        lo_ok = lane_b;
+                        hi_ok = lane < 31 && 2 * lane + 2 >= LEVELS && 2 * lane + 2 <= 63 - LEVELS;
+                    }
+                    if (lo_ok && hi_ok) st2(dst, lo, hi);
+                    else if (lo_ok) st1(dst, lo);
+                    else if (hi_ok) st1(dst + 1, hi);
+                }
+            } else {
+                // strip touches a node that is not deep (domain edge, obstacle, ring)
+#pragma unroll
+                for (int k = 0; k < Q; ++k) {
+                    double *dst = a.fout + k * plane + idx + d_cx[k] * pitch + d_cy[k];
+                    if (da) st1(dst, ha[k]);
+                    if (db) st1(dst + 1, hb[k]);
+                }
             }
         }
+        if (!work_counter) return;
     }
 }
 
@@ -971,12 +988,31 @@ int fused_strips(const Layout &L, int depth)
 
 template <int C, int F, int D>
 static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
-                      int64_t x_end, int32_t rows_per_chunk, cudaStream_t st)
+                      int64_t x_end, int32_t rows_per_chunk, unsigned *work_counter,
+                      cudaStream_t st)
 {
     const int32_t strips = fused_strips(a.p.L, D);
     const int64_t chunks = (x_end - x_begin + rows_per_chunk - 1) / rows_per_chunk;
-    const int64_t warps = chunks * strips;
+    int64_t warps = chunks * strips;
     constexpr int wpb = PLB_FUSED_BLOCK / 32;
+    if (work_counter) {
+        // persistent grid: as many CTAs as are resident at once
+        static int resident = 0;
+        if (!resident) {
+#ifdef PLB_EMU_RUNTIME
+            resident = 8;
+#else
+            int per_sm = 0, dev = 0, sms = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bulk_fused<C, F, D>,
+                                                          PLB_FUSED_BLOCK, 0);
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            resident = std::max(1, per_sm * sms);
+#endif
+        }
+        warps = std::min<int64_t>(warps, int64_t(resident) * wpb);
+        cudaMemsetAsync(work_counter, 0, sizeof(unsigned), st);
+    }
 #if PLB_FUSED_STAGES >= 2 && !defined(PLB_EMU_RUNTIME)
     // the prefetch ring wants shared memory, nothing here wants L1
     static bool carveout_set = false;
@@ -989,20 +1025,22 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
 #endif
     PLB_LAUNCH(COOP, (k_bulk_fused<C, F, D>), unsigned((warps + wpb - 1) / wpb),
                PLB_FUSED_BLOCK, st, a, deep, x_begin, x_end, strips,
-               rows_per_chunk);
+               rows_per_chunk, work_counter);
 }
 
 int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
                       int64_t x_begin, int64_t x_end, int32_t rows_per_chunk,
-                      cudaStream_t stream)
+                      unsigned *work_counter, cudaStream_t stream)
 {
     if (x_end <= x_begin || depth < 2 || depth > 3) return 0;
 #define PLB_CASE(C, F)                                                        \
     if (a.collision == C && a.forcing == F) {                                 \
         if (depth == 2)                                                       \
-            run_fused<C, F, 2>(a, deep, x_begin, x_end, rows_per_chunk, stream); \
+            run_fused<C, F, 2>(a, deep, x_begin, x_end, rows_per_chunk,       \
+                               work_counter, stream);                         \
         else                                                                  \
-            run_fused<C, F, 3>(a, deep, x_begin, x_end, rows_per_chunk, stream); \
+            run_fused<C, F, 3>(a, deep, x_begin, x_end, rows_per_chunk,       \
+                               work_counter, stream);                         \
         return 1;                                                             \
     }
     PLB_CASE(0, 0) PLB_CASE(0, 1) PLB_CASE(0, 2)

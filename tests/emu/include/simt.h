@@ -105,6 +105,12 @@ static inline long long clock64() { return plb_emu::clock_ticks(); }
 static inline void __nanosleep(unsigned) { plb_emu::sleep_hook(); }
 static inline void __threadfence_system() {}
 static inline void __threadfence() {}
+static inline unsigned atomicAdd(unsigned *p, unsigned v)
+{
+    const unsigned old = *p;
+    *p = old + v;
+    return old;
+}
 static inline unsigned long long atomicExch(unsigned long long *p,
                                             unsigned long long v)
 {

@@ -42,6 +42,7 @@ def emu(emu_lib, monkeypatch):
     monkeypatch.delenv("PLB_FUSED_ROWS", raising=False)
     monkeypatch.delenv("PLB_FUSE_DEPTH", raising=False)
     monkeypatch.delenv("PLB_EMU_BLOCK_ORDER", raising=False)
+    monkeypatch.delenv("PLB_FUSED_DYNAMIC", raising=False)
     monkeypatch.delenv("PLB_KERNEL", raising=False)
     return monkeypatch
 
@@ -156,6 +157,9 @@ def _run(sim_factory, n_steps, fuse, emu, rows=None, one_by_one=False, depth=2):
     # CTAs last to first for the chunked runs: a result that depended on the
     # order of the CTAs would have two writers for one slot
     emu.setenv("PLB_EMU_BLOCK_ORDER", "reverse" if rows in (5, 7) else "forward")
+    # ... and the one-step-per-call runs draw their work items from the queue
+    # of the persistent-grid variant (PLB_FUSED_DYNAMIC=1)
+    emu.setenv("PLB_FUSED_DYNAMIC", "1" if one_by_one else "0")
     s = make_solver(sim_factory())
     try:
         if one_by_one:
