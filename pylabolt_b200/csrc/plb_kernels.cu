@@ -329,6 +329,17 @@ __host__ __device__ constexpr int fused_span(int depth) { return 64 - 2 * (depth
 #ifndef PLB_FUSED_STAGES
 #define PLB_FUSED_STAGES 2
 #endif
+// PLB_FUSED_BULK=1 (tuning variant, needs PLB_FUSED_STAGES >= 2): the ring is
+// filled by the TMA unit instead of per-lane cp.async -- a warp's row is nine
+// contiguous runs of 512 bytes, so one elected lane issues nine cp.async.bulk
+// copies that complete on a per-warp, per-slot mbarrier (no LSU instruction,
+// no address arithmetic in the other 31 lanes).
+#ifndef PLB_FUSED_BULK
+#define PLB_FUSED_BULK 0
+#endif
+#if PLB_FUSED_BULK && PLB_FUSED_STAGES < 2
+#error "PLB_FUSED_BULK needs a ring (PLB_FUSED_STAGES >= 2)"
+#endif
 
 // Resident CTAs per SM asked of ptxas, per collision model (PLB_FUSED_MINBLOCKS
 // for all, PLB_FUSED_MINBLOCKS_BGK for the reference-ordered BGK kernels, which
@@ -369,6 +380,72 @@ __device__ __forceinline__ void cp_async_wait()
 {
 #ifndef PLB_EMU_RUNTIME
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// ---- TMA bulk copies completing on an mbarrier (PLB_FUSED_BULK) ------------
+// The emulation copies at issue time; there the warp-level barrier that
+// stands in for the wait orders the elected lane's copy before the reads.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar)
+{
+#ifdef PLB_EMU_RUNTIME
+    *bar = 0;
+#else
+    const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+#endif
+}
+__device__ __forceinline__ void mbar_init_fence()
+{
+#ifndef PLB_EMU_RUNTIME
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+#ifndef PLB_EMU_RUNTIME
+    const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b),
+                 "r"(bytes)
+                 : "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes,
+                                         unsigned long long *bar)
+{
+#ifdef PLB_EMU_RUNTIME
+    const char *src = static_cast<const char *>(gmem);
+    char *dst = static_cast<char *>(smem);
+    for (unsigned i = 0; i < bytes; ++i) dst[i] = src[i];
+#else
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(d), "l"(gmem), "r"(bytes), "r"(b)
+        : "memory");
+#endif
+}
+// Waits for the phase of `bar` with the given parity.  A copy that never
+// completes traps after ~1 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+#ifdef PLB_EMU_RUNTIME
+    __syncwarp();
+#else
+    const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    unsigned done = 0;
+    for (unsigned spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(b), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (spins > (1u << 20)) __trap();
+    }
 #endif
 }
 
@@ -418,7 +495,21 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
     const Layout &L = a.p.L;
     const int lane = threadIdx.x & 31;
 #if PLB_FUSED_STAGES >= 2
-    __shared__ double2 ring[PLB_FUSED_STAGES][Q][PLB_FUSED_BLOCK];
+    __shared__ __align__(128) double2 ring[PLB_FUSED_STAGES][Q][PLB_FUSED_BLOCK];
+#endif
+#if PLB_FUSED_BULK
+    // one mbarrier per warp and slot; `filled` counts the rows this warp has
+    // sent through the ring since the kernel began (slot = filled % STAGES,
+    // phase parity = filled / STAGES & 1), across work items
+    __shared__ unsigned long long ring_bar[PLB_FUSED_STAGES][PLB_FUSED_BLOCK / 32];
+    const int wid = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < PLB_FUSED_STAGES; ++st) mbar_init(&ring_bar[st][wid]);
+        mbar_init_fence();
+    }
+    __syncwarp();
+    unsigned filled = 0;
 #endif
     // One work item = one chunk of rows of one strip.  Statically a warp takes
     // the item of its own number; with a work counter (PLB_FUSED_DYNAMIC=1,
@@ -451,7 +542,30 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         // row pushed into B in iteration i is x = xs + i - 2 LEVELS.
         const int n_rows = int(xe - xs) + 2 * LEVELS;
         const double *row0 = a.fin + L.at(xs - LEVELS, y);     // pair of row i = 0
-#if PLB_FUSED_STAGES >= 2
+#if PLB_FUSED_BULK
+        constexpr int AHEAD = PLB_FUSED_STAGES - 1;
+        // bytes of the warp's run that lie inside the padded row (the lanes
+        // with in_row are a prefix of the warp), and the elected lane's view
+        // of the run
+        const unsigned run_bytes = 16u * unsigned(__popc(__ballot_sync(0xffffffffu, in_row)));
+        const double *run0 = row0 - 2 * lane;
+        // row number j of this item into its slot; the slot was last read one
+        // iteration ago by every lane (__syncwarp: those reads are done)
+        auto fill = [&](int j) {
+            __syncwarp();
+            if (lane == 0 && run_bytes != 0 && j < n_rows) {
+                const unsigned g = filled + unsigned(j);
+                unsigned long long *bar = &ring_bar[g % PLB_FUSED_STAGES][wid];
+                mbar_expect_tx(bar, Q * run_bytes);
+#pragma unroll
+                for (int k = 0; k < Q; ++k)
+                    bulk_g2s(&ring[g % PLB_FUSED_STAGES][k][wid * 32],
+                             run0 + k * plane + int64_t(j) * pitch, run_bytes, bar);
+            }
+        };
+#pragma unroll
+        for (int i = 0; i < AHEAD; ++i) fill(i);
+#elif PLB_FUSED_STAGES >= 2
         constexpr int AHEAD = PLB_FUSED_STAGES - 1;
 #pragma unroll
         for (int i = 0; i < AHEAD; ++i) {
@@ -481,7 +595,22 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
                 dd_next = *reinterpret_cast<const uint16_t *>(
                     deep + L.at(xs + i + 1 - 2 * LEVELS, y));
             double fa[Q], fb[Q];
-#if PLB_FUSED_STAGES >= 2
+#if PLB_FUSED_BULK
+            {
+                fill(i + AHEAD);            // the slot read in the previous iteration
+                const unsigned g = filled + unsigned(i);
+                const int slot = int(g % PLB_FUSED_STAGES);
+                if (run_bytes != 0)         // row i has landed
+                    mbar_wait(&ring_bar[slot][wid], (g / PLB_FUSED_STAGES) & 1u);
+#pragma unroll
+                for (int k = 0; k < Q; ++k) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (in_row) v = ring[slot][k][threadIdx.x];
+                    fa[k] = v.x;
+                    fb[k] = v.y;
+                }
+            }
+#elif PLB_FUSED_STAGES >= 2
             {
                 // refill the slot that was read in the previous iteration
                 const int j = i + AHEAD;
@@ -585,6 +714,9 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
             }
         }
         if (!work_counter) return;
+#if PLB_FUSED_BULK
+        if (run_bytes != 0) filled += unsigned(n_rows);
+#endif
     }
 }
 

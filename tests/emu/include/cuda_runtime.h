@@ -23,6 +23,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 // ---- vector types ------------------------------------------------------------
 struct alignas(16) double2 { double x, y; };

@@ -105,6 +105,8 @@ static inline long long clock64() { return plb_emu::clock_ticks(); }
 static inline void __nanosleep(unsigned) { plb_emu::sleep_hook(); }
 static inline void __threadfence_system() {}
 static inline void __threadfence() {}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+[[noreturn]] static inline void __trap() { __builtin_trap(); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v)
 {
     const unsigned old = *p;

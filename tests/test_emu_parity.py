@@ -313,3 +313,30 @@ def test_residues_and_link_record_with_pairing(emu):
     finally:
         a.close()
         b.close()
+
+
+# ---- tuning variants of the fused kernel (tools/build_variants.py) ------------
+@pytest.fixture(scope="module")
+def emu_bulk_lib():
+    """PLB_FUSED_BULK=1: the prefetch ring filled by TMA bulk copies that
+    complete on per-warp mbarriers (three slots)."""
+    return build_emu.build(variant="bulk_s3", extra_flags=["-DPLB_FUSED_BULK=1",
+                                                           "-DPLB_FUSED_STAGES=3"])
+
+
+@pytest.mark.parametrize("name", ["mrt_poiseuille_70x140_guo2", "cylinder_120x140",
+                                  "poiseuille_9x300_none"])
+def test_bulk_copy_ring_variant_equals_single_steps(emu, emu_bulk_lib, name):
+    """Slot / phase bookkeeping of the mbarrier ring: chunks shorter than the
+    ring, work items drawn from the queue (the running fill count crosses
+    items), both depths -- bit for bit against the single-step path."""
+    factory = WIDE_CASES[name]
+    want, _ = _run(factory, 15, "0", emu)
+    emu.setenv("PLB_LIB", emu_bulk_lib)
+    for rows, one_by_one, depth in ((None, False, 2), (1, False, 2), (64, True, 2),
+                                    (7, True, 3)):
+        got, info = _run(factory, 15, "2", emu, rows=rows, one_by_one=one_by_one,
+                         depth=depth)
+        assert info["pairs"] + info["triples"] > 0, info
+        for key in ("density", "velocity", "pop_fluid_new"):
+            assert np.array_equal(got[key], want[key]), (name, rows, depth, key)

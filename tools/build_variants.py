@@ -23,6 +23,13 @@ VARIANTS = {
     "d3_s3_b64_mb5": ["-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=6",
                       "-DPLB_FUSED_MINBLOCKS_D3=5"],
     "d3_mb3": ["-DPLB_FUSED_MINBLOCKS_D3=3"],
+    # ring filled by TMA bulk copies on per-warp mbarriers (no LSU instruction,
+    # no destination registers): 2 / 3 / 4 slots, and four CTAs per SM for the
+    # kernels that then fit 128 registers
+    "bulk_s2": ["-DPLB_FUSED_BULK=1"],
+    "bulk_s3": ["-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=3"],
+    "bulk_s4": ["-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=4"],
+    "bulk_s3_mb4": ["-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_MINBLOCKS=4"],
 }
 
 if __name__ == "__main__":
