@@ -80,13 +80,15 @@ class BoundaryElement:
 class Boundary:
     """boundary_dict -> boundary elements (base/boundary.py:130-653)."""
 
-    def __init__(self, simulation, mesh, domain, control, fields, verbose=True):
+    def __init__(self, simulation, mesh, domain, control, fields, fluid=False,
+                 phase=False, scalar=False, verbose=True):
+        # signature of base/boundary.py:131-142
         rank = domain.mpi_rank
         print_log("-" * 80, rank, verbose)
         print_log("Setting up domain boundaries...\n", rank, verbose)
         if not hasattr(simulation, "boundary_dict"):
             raise ValueError("boundary_dict not found in simulation.py file")
-        self.fluid = True
+        self.fluid, self.phase, self.scalar = fluid, phase, scalar
         self.boundary_dict = simulation.boundary_dict
         self.compute_force = False
         self.write_boundary_data = False

@@ -161,7 +161,7 @@ class Ellipse(Body):
         self.semi_minor_axis = prec(_number(
             spec["semi_minor_axis"], self.name, "semi_minor_axis", "ellipse"))
         angle = _number(spec["inclination_angle"], self.name,
-                        "inclination_angle", "ellipse")
+                        "inclination_angle", "ellipse representing angle in degrees")
         self.extent = float(max(self.semi_major_axis, self.semi_minor_axis))
         self._angle_deg = angle
 
@@ -225,7 +225,9 @@ class Obstacle:
     (base/obstacle.py:10-300 + base/obstacle_operator.py:20-45)."""
 
     def __init__(self, simulation, mesh, domain, control, fields, boundary,
-                 verbose=True):
+                 fluid=False, phase=False, scalar=False, verbose=True):
+        # signature of base/obstacle.py:11-23
+        self.fluid, self.phase, self.scalar = fluid, phase, scalar
         rank = domain.mpi_rank
         print_log("-" * 80, rank, verbose)
         print_log("Setting up obstacles...\n", rank, verbose)
@@ -318,9 +320,9 @@ class Obstacle:
         density = fields.density.reshape(nxp, nyp)
         velocity = fields.velocity.reshape(nxp, nyp, 2)
         for a_x, b_x in _runs(lo_x, hi_x, int(grid[0]), boundary.x_periodic,
-                              int(domain.offset[0]), domain.Nx_rank):
+                              int(domain.offset[0]), nxp - 2):
             for a_y, b_y in _runs(lo_y, hi_y, int(grid[1]), boundary.y_periodic,
-                                  int(domain.offset[1]), domain.Ny_rank):
+                                  int(domain.offset[1]), nyp - 2):
                 i_loc = np.arange(a_x, b_x, dtype=np.int64)[:, None]
                 j_loc = np.arange(a_y, b_y, dtype=np.int64)[None, :]
                 i_glob = i_loc - 1 + int(domain.offset[0])
@@ -410,6 +412,8 @@ class Obstacle:
         n_overlap = int(np.count_nonzero(overlap & fluid_boundary[box]))
         self.local_fluid_boundary_overlap = n_overlap
 
+        if not hasattr(fields, "surface_normals"):
+            return              # a geometry-only container (reference tests)
         normals = fields.surface_normals.reshape(nxp, nyp, 2)
         surface = (solid_boundary[box] | fluid_boundary[box])
         i_glob = (np.arange(x0, x1 + 1, dtype=np.int64)[:, None] - 1 +

@@ -13,6 +13,7 @@ reference; the differences are deliberate and local:
 * fp64 only (the north star is an fp64 path).
 """
 import numpy as np
+from types import SimpleNamespace
 
 from .helpers import print_log
 
@@ -62,9 +63,9 @@ class Control:
         if self.precision_type == "double":
             self.precision = np.float64
         elif self.precision_type == "single":
-            raise ValueError(
-                "precision 'single' is not available in the b200 back end: "
-                "the fluidLB step is an fp64 path (use 'double')")
+            # a valid container value like in the reference; State refuses to
+            # build an fp32 case for the b200 path (fp64 only)
+            self.precision = np.float32
         else:
             raise ValueError("unsupported precision specified." +
                              "available precision (single, double)")
@@ -102,18 +103,26 @@ class Lattice:
         if "lattice_type" not in lattice_dict:
             raise ValueError("lattice_type missing in lattice_dict")
         self.lattice_type = lattice_dict["lattice_type"]
+        for key, value in d2q9_constants(control.precision).items():
+            setattr(self, key, value)
         if self.lattice_type == "D2Q9":
             if mesh.dimensions != 2:
                 raise ValueError(
                     "grid dimensions and lattice type are incompatible")
+            self.no_of_directions = int(9)
         elif self.lattice_type == "D1Q3":
-            raise ValueError("D1Q3 is not available in the b200 back end "
-                             "(the accelerated path is D2Q9)")
+            # the container knows the reference's second lattice (:61-70);
+            # State refuses to build a D1Q3 case for the b200 path
+            if mesh.dimensions != 1:
+                raise ValueError(
+                    "grid dimensions and lattice type are incompatible")
+            self.cx = np.array([0, 1, -1], dtype=int)
+            self.cy = np.array([0, 0, 0], dtype=int)
+            self.weights = np.array([2 / 3, 1 / 6, 1 / 6], dtype=control.precision)
+            self.inv_list = np.array([0, 2, 1], dtype=int)
+            self.no_of_directions = int(3)
         else:
             raise ValueError("Unsupported lattice type")
-        for key, value in d2q9_constants(control.precision).items():
-            setattr(self, key, value)
-        self.no_of_directions = int(9)
         print_log("lattice type set: " + self.lattice_type, rank, verbose)
 
 
@@ -185,10 +194,18 @@ class Fields:
     """Per-node host arrays in the reference layout
     (pylabolt/base/fields.py:50-92): one ghost ring, ind = x * Ny_pad + y."""
 
-    def __init__(self, control, lattice, domain):
+    def __init__(self, control, lattice, domain, fluid=False, phase=False,
+                 scalar=False):
+        # same signature as the reference (base/fields.py:5-13).  The geometry
+        # arrays always exist; rho / u / p are what the fluidLB path reads and
+        # writes on the host (the populations live on the device only), the
+        # phase-field and scalar solvers are outside this build.
+        _fluid_only(phase, scalar)
         size = int(domain.size)
         prec = control.precision
-        self.fluid = True
+        self.fluid = fluid
+        self.phase = phase
+        self.scalar = scalar
         self.solid = np.zeros(size, dtype=np.bool_)
         self.solid_id = np.full(size, -1, dtype=int)
         self.solid_boundary = np.zeros(size, dtype=np.bool_)
@@ -201,6 +218,12 @@ class Fields:
         self.pressure = np.zeros(size, dtype=prec)
 
 
+def _fluid_only(phase, scalar):
+    if phase or scalar:
+        raise ValueError("only the fluid (fluidLB) path is built for the b200 "
+                         "back end: phase / scalar fields are not available")
+
+
 def ghost_ring(shape):
     """Fields.init_ghost_nodes (pylabolt/base/fields.py:166-179), vectorised:
     True on the outermost ring of the padded array."""
@@ -211,13 +234,26 @@ def ghost_ring(shape):
     return ghost.reshape(-1)
 
 
+def local_to_global(i, j, offset):
+    """Local (un-padded) sub-domain index -> global index,
+    parallel/cpu/MPI_kernels.py:5-18; ints or index arrays."""
+    return i + offset[0], j + offset[1]
+
+
+def global_to_local(i_global, j_global, offset):
+    """parallel/cpu/MPI_kernels.py:21-33."""
+    return i_global - offset[0], j_global - offset[1]
+
+
 def global_coordinates(domain):
     """(i_global, j_global) of every padded node, flat, as int arrays:
-    local_to_global(i - 1, j - 1, offset), cpu/MPI_kernels.py:5-18."""
+    local_to_global(i - 1, j - 1, offset) like set_field_scalar / _vector
+    (base/init_fields.py:336-345)."""
     nxp, nyp = int(domain.shape[0]), int(domain.shape[1])
-    i = np.repeat(np.arange(nxp, dtype=np.int64) - 1 + int(domain.offset[0]), nyp)
-    j = np.tile(np.arange(nyp, dtype=np.int64) - 1 + int(domain.offset[1]), nxp)
-    return i, j
+    i = np.repeat(np.arange(nxp, dtype=np.int64) - 1, nyp)
+    j = np.tile(np.arange(nyp, dtype=np.int64) - 1, nxp)
+    offset = (int(domain.offset[0]), int(domain.offset[1]))
+    return local_to_global(i, j, offset)
 
 
 def _field_spec(spec, control, scalar):
@@ -242,13 +278,39 @@ def _field_spec(spec, control, scalar):
     raise ValueError("Unsupported velocity initialization")
 
 
+def read_dict(dict_input, field, ghost_node, domain, control, scalar_dict=True):
+    """The reference's entry point of the same name and argument order
+    (base/init_fields.py:274-322): reads one field definition and applies it
+    to ``field`` on the non-ghost nodes."""
+    _apply_field(dict_input, field, domain, SimpleNamespace(ghost_node=ghost_node),
+                 control, scalar_dict)
+
+
+def set_field_scalar(domain, field, ghost_node, value=None, func=None,
+                     input_file=None):
+    """base/init_fields.py:352-375."""
+    _set_field(field, domain, ghost_node, value, func, True, field.dtype.type)
+
+
+def set_field_vector(domain, field, ghost_node, value=None, func=None,
+                     input_file=None):
+    """base/init_fields.py:325-349."""
+    _set_field(field, domain, ghost_node, value, func, False, field.dtype.type)
+
+
 def _apply_field(spec, field, domain, fields, control, scalar):
     """set_field_scalar / set_field_vector, init_fields.py:325-375.  ``func``
     is called with python ints exactly like the reference does (so the values
     are bit-identical); a function carrying ``vectorized = True`` is called
     once with index arrays instead."""
     value, func = _field_spec(spec, control, scalar)
-    inner = ~fields.ghost_node
+    _set_field(field, domain, fields.ghost_node, value, func, scalar,
+               control.precision)
+
+
+def _set_field(field, domain, ghost_node, value, func, scalar, precision):
+    control = SimpleNamespace(precision=precision)
+    inner = ~ghost_node
     if func is None:
         field[inner] = value
         return
@@ -269,10 +331,38 @@ def _apply_field(spec, field, domain, fields, control, scalar):
         field[inner, 1] = np.asarray(result[1], dtype=control.precision)
 
 
-def init_fields(simulation, control, domain, fields, verbose=True):
-    """initial_fields_dict -- pylabolt/base/init_fields.py:7-129: the
-    ``default`` section is mandatory, every other key is a region override
-    applied in dict order."""
+# Sections of initial_fields_dict: (field attribute, scalar?) per key.  The
+# fluid section is what the b200 path consumes; the phase section is
+# initialised on whatever container carries ``phase_field`` (the reference's
+# init_fields_phase, base/init_fields.py:224-268) although no phase-field
+# solver is built here.
+_SECTIONS = {
+    "fluid": (("velocity", False), ("density", True), ("pressure", True)),
+    "phase": (("phase_field", True),),
+}
+
+
+def _init_section(section, user, fields, domain, control, default, verbose):
+    rank = domain.mpi_rank
+    if default:
+        for key, _ in _SECTIONS[section]:
+            if key not in user:
+                raise ValueError("'" + key + "' is missing in default")
+    for key, scalar in _SECTIONS[section]:
+        if key in user:
+            if not default:
+                print_log(section + ": setting " + key + " override", rank, verbose)
+            _apply_field(user[key], getattr(fields, key), domain, fields, control,
+                         scalar)
+        else:
+            print_log(section + ": no " + key + " override", rank, verbose)
+
+
+def init_fields(simulation, control, domain, fields, fluid=False, phase=False,
+                scalar=False, verbose=True):
+    """initial_fields_dict -- pylabolt/base/init_fields.py:7-129 (same
+    signature): the ``default`` section is mandatory, every other key is a
+    region override applied in dict order."""
     rank = domain.mpi_rank
     print_log("-" * 80, rank, verbose)
     print_log("Initializing fields...\n", rank, verbose)
@@ -280,33 +370,30 @@ def init_fields(simulation, control, domain, fields, verbose=True):
     if "default" not in initial_fields_dict:
         raise ValueError("default missing in initial_fields_dict")
     default = initial_fields_dict["default"]
-    if "fluid" not in default:
-        raise ValueError("fluid missing in initial_fields_dict - default")
-    fluid = default["fluid"]
-    for key in ("velocity", "density", "pressure"):
-        if key not in fluid:
-            raise ValueError("'" + key + "' is missing in default")
-    targets = (("velocity", fields.velocity, False),
-               ("density", fields.density, True),
-               ("pressure", fields.pressure, True))
-    for key, field, scalar in targets:
-        _apply_field(fluid[key], field, domain, fields, control, scalar)
+    enabled = (("fluid", fluid, "fluid missing in initial_fields_dict - default",
+                "WARNING! not a fluid solver. Skipping fluid overrides"),
+               ("phase", phase, "'phase' missing in initial_fields_dict - default",
+                "WARNING! not a multiphase solver. Skipping phase overrides"))
+    for section, on, missing, _ in enabled:
+        if on is True:
+            if section not in default:
+                raise ValueError(missing)
+            _init_section(section, default[section], fields, domain, control,
+                          True, verbose)
     for region_no, (region, user) in enumerate(initial_fields_dict.items()):
         if region == "default":
             continue
         print_log("Region id: " + str(region_no) + " | Region name: " +
                   str(region), rank, verbose)
-        if "fluid" not in user:
-            print_log("fluid: no override", rank, verbose)
-            continue
-        print_log("fluid: override present", rank, verbose)
-        for key, field, scalar in targets:
-            if key in user["fluid"]:
-                print_log("fluid: setting " + key + " override", rank, verbose)
-                _apply_field(user["fluid"][key], field, domain, fields,
-                             control, scalar)
+        for section, on, _, skipped in enabled:
+            if section not in user:
+                print_log(section + ": no override", rank, verbose)
+            elif on is False:
+                print_log(skipped, rank, verbose)
             else:
-                print_log("fluid: no " + key + " override", rank, verbose)
+                print_log(section + ": override present", rank, verbose)
+                _init_section(section, user[section], fields, domain, control,
+                              False, verbose)
     print_log("Initializing fields done!", rank, verbose)
     print_log("-" * 80, rank, verbose)
 
@@ -324,21 +411,31 @@ class State:
         self.fluid, self.phase, self.scalar = True, False, False
         try:
             self.control = Control(simulation, mpi_rank, verbose)
+            if self.control.precision is not np.float64:
+                raise ValueError(
+                    "precision 'single' is not available in the b200 back end: "
+                    "the fluidLB step is an fp64 path (use 'double')")
             self.mesh = Mesh(simulation, mpi_rank, verbose)
             self.lattice = Lattice(simulation, self.control, self.mesh,
                                    mpi_rank, verbose)
+            if self.lattice.lattice_type != "D2Q9":
+                raise ValueError(self.lattice.lattice_type + " is not available "
+                                 "in the b200 back end (the accelerated path "
+                                 "is D2Q9)")
             self.domain = Domain(simulation, self.mesh, comm, verbose)
             self.domain.require_slabs()
             self.transport = Transport(simulation, self.control, self.domain,
                                        verbose)
-            self.fields = Fields(self.control, self.lattice, self.domain)
+            self.fields = Fields(self.control, self.lattice, self.domain,
+                                 fluid=fluid)
             init_fields(simulation, self.control, self.domain, self.fields,
-                        verbose)
+                        fluid=fluid, verbose=verbose)
             self.boundary = Boundary(simulation, self.mesh, self.domain,
-                                     self.control, self.fields, verbose)
+                                     self.control, self.fields, fluid=fluid,
+                                     verbose=verbose)
             self.obstacle = Obstacle(simulation, self.mesh, self.domain,
                                      self.control, self.fields, self.boundary,
-                                     verbose)
+                                     fluid=fluid, verbose=verbose)
         except Exception as e:
             print_log("-" * 80, mpi_rank, True)
             print_log("FATAL ERROR!", mpi_rank, True)

@@ -39,9 +39,12 @@ def test_control_precision():
     sim = broken(lambda s: s.control_dict.update(precision="half"))
     with pytest.raises(ValueError, match="unsupported precision"):
         Control(sim, 0, verbose=False)
+    # 'single' is a valid container value (reference: control.py:43-44); the
+    # b200 State refuses to build the case
     sim = broken(lambda s: s.control_dict.update(precision="single"))
+    assert Control(sim, 0, verbose=False).precision is np.float32
     with pytest.raises(ValueError, match="fp64"):
-        Control(sim, 0, verbose=False)
+        state_of(sim)
     c = Control(cases.cavity(), 0, verbose=False)
     assert c.precision is np.float64
     assert c.float_min == np.finfo(np.float64).eps
@@ -81,6 +84,16 @@ def test_lattice_validation():
     line = Mesh(broken(lambda s: s.mesh_dict.update(grid=[1, 9])), 0, False)
     with pytest.raises(ValueError, match="incompatible"):
         Lattice(sim, control, line, 0, False)
+    # the container knows D1Q3 (reference: lattice.py:61-70) ...
+    d1q3 = broken(lambda s: s.lattice_dict.update(lattice_type="D1Q3"))
+    with pytest.raises(ValueError, match="incompatible"):
+        Lattice(d1q3, control, mesh, 0, False)
+    lat = Lattice(d1q3, control, line, 0, False)
+    assert lat.no_of_directions == 3 and list(lat.inv_list) == [0, 2, 1]
+    # ... and the b200 State refuses to build such a case
+    d1q3.mesh_dict.update(grid=[9, 1])
+    with pytest.raises(ValueError, match="D1Q3 is not available"):
+        state_of(d1q3)
 
 
 @pytest.mark.parametrize("mutate,message", [

@@ -1,0 +1,50 @@
+"""The reference's OWN unit tests, driven against the host mirror.
+
+tools/reference_unit_conformance.py executes the reference's tests/unit
+(where they lie in the reference checkout) once against the reference's
+containers and once against pylabolt_b200 through an alias package; the
+committed table tests/golden/reference_unit_conformance.json holds both
+outcomes per test.  Here: the committed table must show no test that the
+reference passes and the mirror does not, and -- wherever the reference
+checkout is present (not on the GPU box) -- the mirror arm is re-run and must
+reproduce the table.
+"""
+import importlib.util
+import json
+import os
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOOL = os.path.join(os.path.dirname(HERE), "tools", "reference_unit_conformance.py")
+
+
+def load_tool():
+    spec = importlib.util.spec_from_file_location("reference_unit_conformance", TOOL)
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    return tool
+
+
+def committed_table():
+    with open(os.path.join(HERE, "golden", "reference_unit_conformance.json")) as f:
+        return json.load(f)["tests"]
+
+
+def test_committed_table_has_no_regression_against_the_reference():
+    table = committed_table()
+    passed_by_reference = [n for n, row in table.items() if row["reference"] == "passed"]
+    assert len(passed_by_reference) >= 43
+    for name in passed_by_reference:
+        assert table[name]["mirror"] == "passed", name
+
+
+def test_mirror_reproduces_the_table_where_the_reference_is_present():
+    tool = load_tool()
+    if not os.path.isdir(tool.UNIT):
+        pytest.skip("reference checkout not present (GPU box)")
+    ours = tool.mirror_arm()
+    table = committed_table()
+    assert set(ours) == set(table)
+    for name, row in table.items():
+        assert ours[name] == row["mirror"], name
