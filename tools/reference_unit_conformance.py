@@ -19,6 +19,15 @@ section 4 -- and fail identically on the mirror, which raises the same
 messages; test_domain.py / test_mpi_operator.py cannot even be imported
 against the reference snapshot and are left out of both arms.)
 
+Second pass, "drift repaired": most of those failures have one cause -- the
+reference's test dictionaries lack the ``wall`` key its Boundary has since
+required.  A pytest plugin (generated here, applied to BOTH arms) fills in
+``wall: False`` before Boundary.__init__ runs.  Then the reference passes 68
+tests, among them the boundary node / direction lists for one and several ranks
+and the periodic pairs (TestBoundaryNodeAllocation), and the mirror must pass
+every one of them except the phase-field boundary sections
+(TestPhaseBoundaryDicts: phaseFieldLB is outside the b200 build).
+
 --write stores the table in tests/golden/reference_unit_conformance.json
 (the CPU test suite checks the committed table, and re-runs the mirror arm
 wherever the reference checkout is present).
@@ -69,6 +78,27 @@ def Finalize(): pass
 '''
 
 
+DRIFT_REPAIR_PLUGIN = '''
+import pytest
+
+
+@pytest.fixture(autouse=True)
+def _wall_key_default(monkeypatch):
+    import pylabolt.base.boundary as module
+    original = module.Boundary.__init__
+
+    def init(self, simulation, *args, **kwargs):
+        boundary_dict = getattr(simulation, "boundary_dict", None)
+        if isinstance(boundary_dict, dict):
+            for name, user in boundary_dict.items():
+                if name != "options" and isinstance(user, dict):
+                    user.setdefault("wall", False)
+        return original(self, simulation, *args, **kwargs)
+    monkeypatch.setattr(module.Boundary, "__init__", init)
+'''
+OUT_OF_SCOPE = "TestPhaseBoundaryDicts"      # phase-field boundary sections
+
+
 def write_tree(root, files):
     for rel, text in files.items():
         path = os.path.join(root, rel)
@@ -81,9 +111,11 @@ def write_tree(root, files):
             open(init, "w").close()
 
 
-def run_arm(python_path):
+def run_arm(python_path, repair=False):
     cmd = [sys.executable, "-m", "pytest", UNIT, "-q", "-p", "no:cacheprovider",
            "-rA", "--tb=no"]
+    if repair:
+        cmd += ["-p", "plb_drift_repair"]
     for name in SKIPPED_MODULES:
         cmd.append("--ignore=" + os.path.join(UNIT, name))
     env = dict(os.environ, PYTHONPATH=os.pathsep.join(python_path + [UNIT]),
@@ -100,23 +132,22 @@ def run_arm(python_path):
     return outcomes
 
 
-def mirror_arm():
+def mirror_arm(repair=False):
     with tempfile.TemporaryDirectory() as shim:
-        write_tree(shim, ALIASES)
-        return run_arm([shim, REPO])
+        write_tree(shim, dict(ALIASES, **{"plb_drift_repair.py": DRIFT_REPAIR_PLUGIN}))
+        return run_arm([shim, REPO], repair)
 
 
-def reference_arm():
+def reference_arm(repair=False):
     with tempfile.TemporaryDirectory() as shim:
         write_tree(shim, {"mpi4py/__init__.py": "def rc(**kw): pass\nfrom . import MPI",
-                          "mpi4py/MPI.py": MPI_STAND_IN})
-        return run_arm([shim, REFERENCE])
+                          "mpi4py/MPI.py": MPI_STAND_IN,
+                          "plb_drift_repair.py": DRIFT_REPAIR_PLUGIN})
+        return run_arm([shim, REFERENCE], repair)
 
 
-def main():
-    if not os.path.isdir(UNIT):
-        raise SystemExit("reference checkout not found at " + REFERENCE)
-    ref, ours = reference_arm(), mirror_arm()
+def compare(repair):
+    ref, ours = reference_arm(repair), mirror_arm(repair)
     table = {name: {"reference": ref.get(name, "missing"),
                     "mirror": ours.get(name, "missing")}
              for name in sorted(set(ref) | set(ours))}
@@ -124,19 +155,30 @@ def main():
     for row in table.values():
         key = row["reference"] + " -> " + row["mirror"]
         count[key] = count.get(key, 0) + 1
+    print("drift repaired:" if repair else "as shipped:")
     for key in sorted(count):
         print(f"{count[key]:4d}  reference {key} (mirror)")
     bad = [n for n, row in table.items()
-           if row["reference"] == "passed" and row["mirror"] != "passed"]
+           if row["reference"] == "passed" and row["mirror"] != "passed"
+           and OUT_OF_SCOPE not in n]
     for name in bad:
         print("NOT CONFORMING:", name)
+    return table, bad
+
+
+def main():
+    if not os.path.isdir(UNIT):
+        raise SystemExit("reference checkout not found at " + REFERENCE)
+    table, bad = compare(False)
+    repaired, bad_repaired = compare(True)
     if "--write" in sys.argv:
         with open(TABLE, "w") as f:
-            json.dump({"skipped_modules": SKIPPED_MODULES, "tests": table}, f,
-                      indent=1, sort_keys=True)
+            json.dump({"skipped_modules": SKIPPED_MODULES,
+                       "out_of_scope": OUT_OF_SCOPE, "tests": table,
+                       "tests_drift_repaired": repaired}, f, indent=1, sort_keys=True)
             f.write("\n")
         print("wrote", os.path.relpath(TABLE, REPO))
-    return 1 if bad else 0
+    return 1 if bad or bad_repaired else 0
 
 
 if __name__ == "__main__":
