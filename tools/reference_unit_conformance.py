@@ -17,7 +17,9 @@ must pass on the mirror.  (About half of the reference's tests fail on the
 reference itself -- its tests drifted from its case-file schema, SURVEY.md
 section 4 -- and fail identically on the mirror, which raises the same
 messages; test_domain.py / test_mpi_operator.py cannot even be imported
-against the reference snapshot and are left out of both arms.)
+against the reference snapshot.  The mirror runs test_domain.py -- its 39
+decomposition tests all pass, "reference: missing" in the table -- and leaves
+out test_mpi_operator.py: the halo exchange lives on the device here.)
 
 Second pass, "drift repaired": most of those failures have one cause -- the
 reference's test dictionaries lack the ``wall`` key its Boundary has since
@@ -111,12 +113,12 @@ def write_tree(root, files):
             open(init, "w").close()
 
 
-def run_arm(python_path, repair=False):
+def run_arm(python_path, repair=False, skipped=tuple(SKIPPED_MODULES)):
     cmd = [sys.executable, "-m", "pytest", UNIT, "-q", "-p", "no:cacheprovider",
            "-rA", "--tb=no"]
     if repair:
         cmd += ["-p", "plb_drift_repair"]
-    for name in SKIPPED_MODULES:
+    for name in skipped:
         cmd.append("--ignore=" + os.path.join(UNIT, name))
     env = dict(os.environ, PYTHONPATH=os.pathsep.join(python_path + [UNIT]),
                PYTHONDONTWRITEBYTECODE="1")
@@ -135,7 +137,9 @@ def run_arm(python_path, repair=False):
 def mirror_arm(repair=False):
     with tempfile.TemporaryDirectory() as shim:
         write_tree(shim, dict(ALIASES, **{"plb_drift_repair.py": DRIFT_REPAIR_PLUGIN}))
-        return run_arm([shim, REPO], repair)
+        # test_domain.py needs local_to_global / global_to_local next to
+        # Domain, which the mirror has and the reference snapshot has not
+        return run_arm([shim, REPO], repair, skipped=SKIPPED_MODULES[1:])
 
 
 def reference_arm(repair=False):
