@@ -31,9 +31,15 @@
 #ifdef PLB_EMU_RUNTIME
 #define PLB_LAUNCH(MODE, KERNEL, GRID, BLOCK, STREAM, ...)                    \
     PLB_EMU_LAUNCH(MODE, (PLB_UNPAREN KERNEL), GRID, BLOCK, STREAM, __VA_ARGS__)
+#define PLB_LAUNCH_SMEM(MODE, KERNEL, GRID, BLOCK, SMEM, STREAM, ...)         \
+    PLB_EMU_LAUNCH(MODE, (PLB_UNPAREN KERNEL), GRID, BLOCK, STREAM, __VA_ARGS__)
 #else
 #define PLB_LAUNCH(MODE, KERNEL, GRID, BLOCK, STREAM, ...)                    \
     PLB_UNPAREN KERNEL<<<(GRID), (BLOCK), 0, (STREAM)>>>(__VA_ARGS__)
+// SMEM bytes of dynamic shared memory (the launcher has raised the kernel's
+// cudaFuncAttributeMaxDynamicSharedMemorySize if that is more than 48 KB)
+#define PLB_LAUNCH_SMEM(MODE, KERNEL, GRID, BLOCK, SMEM, STREAM, ...)         \
+    PLB_UNPAREN KERNEL<<<(GRID), (BLOCK), (SMEM), (STREAM)>>>(__VA_ARGS__)
 #endif
 
 namespace plb {
@@ -340,6 +346,32 @@ __host__ __device__ constexpr int fused_span(int depth) { return 64 - 2 * (depth
 #if PLB_FUSED_BULK && PLB_FUSED_STAGES < 2
 #error "PLB_FUSED_BULK needs a ring (PLB_FUSED_STAGES >= 2)"
 #endif
+// PLB_FUSED_CARRY_SMEM=1 (tuning variant): the post-collision populations that
+// wait one or two iterations for their row (FusedCarry: 18 doubles per lane and
+// level) live in shared memory instead of registers -- every lane reads and
+// writes only its own 16-byte slots, once per iteration, so no barrier is
+// needed and the accesses are conflict free.  Frees ~36 registers per level:
+// two steps per pass then fit 128 registers (four CTAs per SM), three steps
+// per pass 168 (three CTAs per SM).
+#ifndef PLB_FUSED_CARRY_SMEM
+#define PLB_FUSED_CARRY_SMEM 0
+#endif
+// Shared memory of one CTA of k_bulk_fused<.., DEPTH>: the ring, the carried
+// populations of DEPTH - 1 levels, the ring's mbarriers.  The shipped build (ring
+// of two rows: 36 KB) declares it statically; a variant that needs more than
+// the 48 KB a kernel may declare statically takes all of it from dynamic
+// shared memory (PLB_FUSED_DYN_SMEM).
+constexpr int FUSED_RING_BYTES = PLB_FUSED_STAGES * Q * PLB_FUSED_BLOCK * 16;
+constexpr int FUSED_CARRY_LEVEL_BYTES = PLB_FUSED_CARRY_SMEM ? Q * PLB_FUSED_BLOCK * 16 : 0;
+constexpr int FUSED_BAR_BYTES = PLB_FUSED_BULK ? PLB_FUSED_STAGES * (PLB_FUSED_BLOCK / 32) * 8 : 0;
+__host__ __device__ constexpr int fused_smem_bytes(int depth)
+{
+    return FUSED_RING_BYTES + (depth - 1) * FUSED_CARRY_LEVEL_BYTES + FUSED_BAR_BYTES;
+}
+#ifndef PLB_FUSED_DYN_SMEM
+#define PLB_FUSED_DYN_SMEM \
+    (PLB_FUSED_CARRY_SMEM || PLB_FUSED_STAGES * Q * PLB_FUSED_BLOCK * 16 > 48 * 1024 - 256)
+#endif
 
 // Resident CTAs per SM asked of ptxas, per collision model (PLB_FUSED_MINBLOCKS
 // for all, PLB_FUSED_MINBLOCKS_BGK for the reference-ordered BGK kernels, which
@@ -494,14 +526,36 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
     constexpr int LEVELS = DEPTH - 1;              // hand-overs in registers
     const Layout &L = a.p.L;
     const int lane = threadIdx.x & 31;
+#if PLB_FUSED_DYN_SMEM
+#ifdef PLB_EMU_RUNTIME
+    static __align__(128) unsigned char fused_smem[fused_smem_bytes(DEPTH)];
+#else
+    extern __shared__ __align__(128) unsigned char fused_smem[];
+#endif
+    typedef double2 RingSlot[Q][PLB_FUSED_BLOCK];
+    RingSlot *ring = reinterpret_cast<RingSlot *>(fused_smem);
+    // per level: slots 0-2 = k 1, 5, 8 of the even rows, 3-5 = of the odd
+    // rows, 6-8 = k 0, 2, 4 of the previous row; (.x, .y) = nodes (y, y + 1).
+    // Whatever an earlier work item left behind is never used: a row is
+    // complete only after this item has written its two predecessors.
+    RingSlot *carry_s = reinterpret_cast<RingSlot *>(fused_smem + FUSED_RING_BYTES);
+    typedef unsigned long long RingBars[PLB_FUSED_BLOCK / 32];
+    RingBars *ring_bar = reinterpret_cast<RingBars *>(
+        fused_smem + FUSED_RING_BYTES + LEVELS * FUSED_CARRY_LEVEL_BYTES);
+    (void)carry_s;
+    (void)ring_bar;
+#else
 #if PLB_FUSED_STAGES >= 2
     __shared__ __align__(128) double2 ring[PLB_FUSED_STAGES][Q][PLB_FUSED_BLOCK];
+#endif
+#if PLB_FUSED_BULK
+    __shared__ unsigned long long ring_bar[PLB_FUSED_STAGES][PLB_FUSED_BLOCK / 32];
+#endif
 #endif
 #if PLB_FUSED_BULK
     // one mbarrier per warp and slot; `filled` counts the rows this warp has
     // sent through the ring since the kernel began (slot = filled % STAGES,
     // phase parity = filled / STAGES & 1), across work items
-    __shared__ unsigned long long ring_bar[PLB_FUSED_STAGES][PLB_FUSED_BLOCK / 32];
     const int wid = threadIdx.x >> 5;
     if (lane == 0) {
 #pragma unroll
@@ -578,6 +632,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         }
 #endif
 
+#if !PLB_FUSED_CARRY_SMEM
         FusedCarry carry[LEVELS];
 #pragma unroll
         for (int l = 0; l < LEVELS; ++l)
@@ -585,6 +640,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
             for (int j = 0; j < 3; ++j)
                 carry[l].pa[j] = carry[l].pb[j] = carry[l].na[j] = carry[l].nb[j] =
                     carry[l].ca[j] = carry[l].cb[j] = 0.0;
+#endif
 
         // deep flags of the row that is pushed in the NEXT iteration: fetched one
         // iteration ahead, so that the vote below never waits for them
@@ -646,6 +702,29 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
                 if (!complete) break;
                 double sa[Q], sb[Q];
                 fused_stage1<COLL, FORCING>(a, fa, fb, sa, sb);
+#if PLB_FUSED_CARRY_SMEM
+                {
+                    double2(*c)[PLB_FUSED_BLOCK] = carry_s[l];
+                    const int two_back = (i & 1) * 3;       // written two iterations ago
+                    const double2 p1 = c[two_back + 0][threadIdx.x];
+                    const double2 p5 = c[two_back + 1][threadIdx.x];
+                    const double2 p8 = c[two_back + 2][threadIdx.x];
+                    const double2 c0 = c[6][threadIdx.x];
+                    const double2 c2 = c[7][threadIdx.x];
+                    const double2 c4 = c[8][threadIdx.x];
+                    c[two_back + 0][threadIdx.x] = make_double2(sa[1], sb[1]);
+                    c[two_back + 1][threadIdx.x] = make_double2(sa[5], sb[5]);
+                    c[two_back + 2][threadIdx.x] = make_double2(sa[8], sb[8]);
+                    c[6][threadIdx.x] = make_double2(sa[0], sb[0]);
+                    c[7][threadIdx.x] = make_double2(sa[2], sb[2]);
+                    c[8][threadIdx.x] = make_double2(sa[4], sb[4]);
+                    // one step later: the populations of the row one back
+                    fa[0] = c0.x; fa[1] = p1.x; fa[2] = c2.x; fa[3] = sa[3]; fa[4] = c4.x;
+                    fa[5] = p5.x; fa[6] = sa[6]; fa[7] = sa[7]; fa[8] = p8.x;
+                    fb[0] = c0.y; fb[1] = p1.y; fb[2] = c2.y; fb[3] = sb[3]; fb[4] = c4.y;
+                    fb[5] = p5.y; fb[6] = sb[6]; fb[7] = sb[7]; fb[8] = p8.y;
+                }
+#else
                 FusedCarry &c = carry[l];
                 // one step later: the populations of the row one back
                 fa[0] = c.ca[0]; fa[1] = c.pa[0]; fa[2] = c.ca[1]; fa[3] = sa[3]; fa[4] = c.ca[2];
@@ -661,6 +740,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
                 c.nb[0] = sb[1]; c.nb[1] = sb[5]; c.nb[2] = sb[8];
                 c.ca[0] = sa[0]; c.ca[1] = sa[2]; c.ca[2] = sa[4];
                 c.cb[0] = sb[0]; c.cb[1] = sb[2]; c.cb[2] = sb[4];
+#endif
                 complete = i >= 2 * (l + 1);
             }
             if (!complete) continue;
@@ -1127,6 +1207,21 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
     const int64_t chunks = (x_end - x_begin + rows_per_chunk - 1) / rows_per_chunk;
     int64_t warps = chunks * strips;
     constexpr int wpb = PLB_FUSED_BLOCK / 32;
+    constexpr int dyn_smem = PLB_FUSED_DYN_SMEM ? fused_smem_bytes(D) : 0;
+#ifndef PLB_EMU_RUNTIME
+    static bool attributes_set = false;
+    if (!attributes_set) {
+        // the prefetch ring wants shared memory, nothing here wants L1
+        if (PLB_FUSED_STAGES >= 2 || PLB_FUSED_CARRY_SMEM)
+            cudaFuncSetAttribute(k_bulk_fused<C, F, D>,
+                                 cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (dyn_smem > 0)
+            cudaFuncSetAttribute(k_bulk_fused<C, F, D>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+        attributes_set = true;
+    }
+#endif
     if (work_counter) {
         // persistent grid: as many CTAs as are resident at once
         static int resident = 0;
@@ -1136,7 +1231,7 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
 #else
             int per_sm = 0, dev = 0, sms = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bulk_fused<C, F, D>,
-                                                          PLB_FUSED_BLOCK, 0);
+                                                          PLB_FUSED_BLOCK, dyn_smem);
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             resident = std::max(1, per_sm * sms);
@@ -1145,19 +1240,9 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
         warps = std::min<int64_t>(warps, int64_t(resident) * wpb);
         cudaMemsetAsync(work_counter, 0, sizeof(unsigned), st);
     }
-#if PLB_FUSED_STAGES >= 2 && !defined(PLB_EMU_RUNTIME)
-    // the prefetch ring wants shared memory, nothing here wants L1
-    static bool carveout_set = false;
-    if (!carveout_set) {
-        cudaFuncSetAttribute(k_bulk_fused<C, F, D>,
-                             cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-        carveout_set = true;
-    }
-#endif
-    PLB_LAUNCH(COOP, (k_bulk_fused<C, F, D>), unsigned((warps + wpb - 1) / wpb),
-               PLB_FUSED_BLOCK, st, a, deep, x_begin, x_end, strips,
-               rows_per_chunk, work_counter);
+    PLB_LAUNCH_SMEM(COOP, (k_bulk_fused<C, F, D>), unsigned((warps + wpb - 1) / wpb),
+                    PLB_FUSED_BLOCK, dyn_smem, st, a, deep, x_begin, x_end, strips,
+                    rows_per_chunk, work_counter);
 }
 
 int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,

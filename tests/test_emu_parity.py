@@ -316,23 +316,34 @@ def test_residues_and_link_record_with_pairing(emu):
 
 
 # ---- tuning variants of the fused kernel (tools/build_variants.py) ------------
-@pytest.fixture(scope="module")
-def emu_bulk_lib():
-    """PLB_FUSED_BULK=1: the prefetch ring filled by TMA bulk copies that
-    complete on per-warp mbarriers (three slots)."""
-    return build_emu.build(variant="bulk_s3", extra_flags=["-DPLB_FUSED_BULK=1",
-                                                           "-DPLB_FUSED_STAGES=3"])
+VARIANT_FLAGS = {
+    # PLB_FUSED_BULK=1: the prefetch ring filled by TMA bulk copies that
+    # complete on per-warp mbarriers (three slots)
+    "bulk_s3": ["-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=3"],
+    # ... and PLB_FUSED_CARRY_SMEM=1: the carried populations in shared memory
+    # (everything in dynamic shared memory)
+    "carry_bulk_s3": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1",
+                      "-DPLB_FUSED_STAGES=3"],
+}
+
+
+@pytest.fixture(scope="module", params=sorted(VARIANT_FLAGS))
+def emu_variant_lib(request):
+    return build_emu.build(variant=request.param,
+                           extra_flags=VARIANT_FLAGS[request.param])
 
 
 @pytest.mark.parametrize("name", ["mrt_poiseuille_70x140_guo2", "cylinder_120x140",
                                   "poiseuille_9x300_none"])
-def test_bulk_copy_ring_variant_equals_single_steps(emu, emu_bulk_lib, name):
-    """Slot / phase bookkeeping of the mbarrier ring: chunks shorter than the
-    ring, work items drawn from the queue (the running fill count crosses
-    items), both depths -- bit for bit against the single-step path."""
+def test_fused_kernel_variants_equal_single_steps(emu, emu_variant_lib, name):
+    """Slot / phase bookkeeping of the mbarrier ring and the odd / even row
+    slots of the shared-memory carry: chunks shorter than the ring, work items
+    drawn from the queue (the running fill count crosses items, stale carry
+    slots of the previous item), both depths -- bit for bit against the
+    single-step path."""
     factory = WIDE_CASES[name]
     want, _ = _run(factory, 15, "0", emu)
-    emu.setenv("PLB_LIB", emu_bulk_lib)
+    emu.setenv("PLB_LIB", emu_variant_lib)
     for rows, one_by_one, depth in ((None, False, 2), (1, False, 2), (64, True, 2),
                                     (7, True, 3)):
         got, info = _run(factory, 15, "2", emu, rows=rows, one_by_one=one_by_one,

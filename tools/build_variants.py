@@ -30,6 +30,20 @@ VARIANTS = {
     "bulk_s3": ["-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=3"],
     "bulk_s4": ["-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=4"],
     "bulk_s3_mb4": ["-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_MINBLOCKS=4"],
+    # carried populations in shared memory (18 KB per level and CTA) instead of
+    # registers: two steps per pass in 122 registers -> four CTAs per SM (16
+    # warps, 55 KB each); three steps per pass in 126 -> three CTAs (12 warps,
+    # 74 KB each).  With the TMA ring on top: 94 / 96 registers.
+    "carry_mb4": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_MINBLOCKS=4",
+                  "-DPLB_FUSED_MINBLOCKS_D3=3"],
+    "carry_bulk_mb4": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1",
+                       "-DPLB_FUSED_MINBLOCKS=4", "-DPLB_FUSED_MINBLOCKS_D3=3"],
+    # 64-thread CTAs: the same warps per SM in twice as many, smaller CTAs
+    # (the tail of a wave and the shared-memory granularity are finer)
+    "carry_bulk_b64_mb8": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1",
+                           "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=8",
+                           "-DPLB_FUSED_MINBLOCKS_D3=6"],
+    "carry_mb3": ["-DPLB_FUSED_CARRY_SMEM=1"],
 }
 
 if __name__ == "__main__":

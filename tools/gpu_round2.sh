@@ -16,7 +16,7 @@ timeout 300 python -m pytest tests/test_gpu_fused.py tests/test_gpu_zz_fused_dep
 el "pytest fused: $(tail -1 $out/${tag}_pytest_fused.log)"
 # 2. two vs three steps per pass, occupancy / ring variants (each line ~7 s)
 timeout 120 python tools/fused_sweep.py $L/libplb.so:PLB_FUSE=0 $L/libplb.so $L/libplb.so:PLB_FUSE_DEPTH=3 > $out/${tag}_sweep.txt 2>&1
-timeout 480 python tools/fused_sweep.py --models mrt \
+timeout 600 python tools/fused_sweep.py --models mrt \
     $L/libplb.so:PLB_FUSE_DEPTH=3,PLB_FUSED_ROWS=16 $L/libplb.so:PLB_FUSE_DEPTH=3,PLB_FUSED_ROWS=64 \
     $V/libplb_d3_b64_mb5.so:PLB_FUSE_DEPTH=3 $V/libplb_d3_s3_b64_mb5.so:PLB_FUSE_DEPTH=3 \
     $V/libplb_d3_mb3.so:PLB_FUSE_DEPTH=3 \
@@ -24,6 +24,10 @@ timeout 480 python tools/fused_sweep.py --models mrt \
     $V/libplb_s2_mb4.so $V/libplb_s0.so \
     $V/libplb_bulk_s2.so $V/libplb_bulk_s3.so $V/libplb_bulk_s4.so $V/libplb_bulk_s3_mb4.so \
     $V/libplb_bulk_s3.so:PLB_FUSE_DEPTH=3 $V/libplb_bulk_s3.so:PLB_FUSED_DYNAMIC=1,PLB_FUSED_ROWS=128 \
+    $V/libplb_carry_mb4.so $V/libplb_carry_bulk_mb4.so $V/libplb_carry_bulk_b64_mb8.so $V/libplb_carry_mb3.so \
+    $V/libplb_carry_mb4.so:PLB_FUSE_DEPTH=3 $V/libplb_carry_bulk_mb4.so:PLB_FUSE_DEPTH=3 \
+    $V/libplb_carry_bulk_b64_mb8.so:PLB_FUSE_DEPTH=3 $V/libplb_carry_bulk_mb4.so:PLB_FUSE_DEPTH=3,PLB_FUSED_ROWS=64 \
+    $V/libplb_carry_bulk_mb4.so:PLB_FUSED_DYNAMIC=1,PLB_FUSED_ROWS=128 \
     $L/libplb.so:PLB_FUSED_DYNAMIC=1 $L/libplb.so:PLB_FUSED_DYNAMIC=1,PLB_FUSED_ROWS=64 \
     $L/libplb.so:PLB_FUSED_DYNAMIC=1,PLB_FUSED_ROWS=128 $L/libplb.so:PLB_FUSED_DYNAMIC=1,PLB_FUSED_ROWS=256 \
     $L/libplb.so:PLB_FUSED_ROWS=64 $L/libplb.so:PLB_FUSED_ROWS=128 \
