@@ -71,6 +71,8 @@ def main():
     ap.add_argument("--ny", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--models", default="mrt,bgk")
+    ap.add_argument("--timeout", type=float, default=90.0,
+                    help="seconds per variant")
     ap.add_argument("variants", nargs="+")
     args = ap.parse_args()
     models = []
@@ -86,9 +88,15 @@ def main():
             env[k] = v
         code = CHILD % {"repo": REPO, "nx": args.nx, "ny": args.ny,
                         "steps": args.steps, "models": repr(models)}
-        proc = subprocess.run([sys.executable, "-c", code], env=env,
-                              capture_output=True, text=True)
         tag = f"{os.path.basename(lib)} {overrides}"
+        try:
+            proc = subprocess.run([sys.executable, "-c", code], env=env,
+                                  capture_output=True, text=True,
+                                  timeout=args.timeout)
+        except subprocess.TimeoutExpired:
+            # a variant that hangs must not eat the GPU budget of the others
+            print(f"{tag:44s} TIMED OUT after {args.timeout} s", flush=True)
+            continue
         if proc.returncode != 0:
             print(f"{tag:44s} FAILED {proc.stderr[-300:]}", flush=True)
             continue
