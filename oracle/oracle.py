@@ -63,10 +63,10 @@ class _Element(ctypes.Structure):
 
 def build(force=False):
     """Compile liboracle.so with oracle/Makefile (gcc, OpenMP, no FMA)."""
-    src = os.path.join(_HERE, "plb_oracle.c")
+    deps = [os.path.join(_HERE, "plb_oracle.c"), os.path.join(_HERE, "Makefile")]
     if (force or not os.path.exists(_LIB_PATH) or
-            os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)):
-        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"],
+            any(os.path.getmtime(_LIB_PATH) < os.path.getmtime(d) for d in deps)):
+        subprocess.check_call(["make", "-B", "-C", _HERE, "liboracle.so"],
                               stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
