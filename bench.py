@@ -406,7 +406,8 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device):
                 "kernel_ms_per_step": bulk_ms_per_step,
                 "kernel_share_of_step": bulk_ms / (ms * 1.0),
                 "peak_source": peak_src,
-                "d2d_copy_gbs_this_box": copy_gbs}
+                "d2d_copy_gbs_this_box": copy_gbs,
+                "kernel_build": plb.build_info()}
 
     # ---- end to end through the public Solver API, host buffers -----------
     size = plb.size

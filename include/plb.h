@@ -237,6 +237,11 @@ int plb_flush_l2(plb_handle h);
  * bytes of a 1 GiB cudaMemcpyAsync, best of 5): the practical HBM ceiling
  * next to which a roofline fraction is read. */
 int plb_copy_bandwidth(plb_handle h, double *gbs);
+/* Compile-time configuration of the kernels in this build of the library
+ * ("fused: block=128 minblocks=3 ring=cp.async stages=2 carry=registers ..."):
+ * which tuning variant a bench line or a sweep was measured with.  Static
+ * string, never NULL. */
+const char *plb_build_info(void);
 
 #ifdef __cplusplus
 }

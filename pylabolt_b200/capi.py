@@ -31,7 +31,7 @@ EXPORTS = [
     "plb_host_alloc", "plb_host_free", "plb_flush_l2",
     "plb_profile_enable", "plb_profile_read", "plb_info",
     "plb_link_nodes", "plb_download_link_exchange", "plb_copy_bandwidth",
-    "plb_device_pci_bus_id", "plb_fused_info",
+    "plb_device_pci_bus_id", "plb_fused_info", "plb_build_info",
 ]
 STORE_MOMENTS, RECORD_LINKS = 1, 2
 # plb_info()["faces"]: how the slab-face populations travel
@@ -109,6 +109,8 @@ def load_library(strict=None):
                                    ctypes.POINTER(i64)]
     lib.plb_download_link_exchange.argtypes = [vp, ctypes.POINTER(dbl), i64]
     lib.plb_copy_bandwidth.argtypes = [vp, ctypes.POINTER(dbl)]
+    lib.plb_build_info.argtypes = []
+    lib.plb_build_info.restype = ctypes.c_char_p
     lib.plb_device_pci_bus_id.argtypes = [i32, ctypes.c_char_p, i32]
     _libs[path] = lib
     return lib
@@ -342,6 +344,10 @@ class Plb:
         keys = ("active", "n_deep", "n_deep3", "n_list1", "pairs", "rows",
                 "strips", "triples")
         return dict(zip(keys, out[:8]))
+
+    def build_info(self):
+        """Compile-time kernel configuration of the loaded library."""
+        return self.lib.plb_build_info().decode()
 
     def copy_bandwidth(self):
         """GB/s (read + write) of a device-to-device copy on this GPU, now."""

@@ -1566,6 +1566,8 @@ int plb_flush_l2(plb_handle s)
     return PLB_OK;
 }
 
+const char *plb_build_info(void) { return kernel_build_info(); }
+
 int plb_copy_bandwidth(plb_handle s, double *gbs)
 {
     if (!s || !gbs) return fail(PLB_ERR_INVALID, "null argument");

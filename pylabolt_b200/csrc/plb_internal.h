@@ -121,6 +121,8 @@ int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
                       int64_t x_begin, int64_t x_end, int32_t rows_per_chunk,
                       unsigned *work_counter, cudaStream_t stream);
 int fused_strips(const Layout &L, int depth);
+// compile-time configuration of the kernels (plb_build_info)
+const char *kernel_build_info();
 // One slab-edge column with the face redirection of StepArgs::face_lo/hi.
 int launch_bulk_edge(const StepArgs &a, int64_t x_begin, int64_t x_end,
                      cudaStream_t stream);

@@ -19,6 +19,7 @@
 //   k_face_unpack               : slab-face / periodic-x delivery of the
 //                                 three populations that cross a face
 #include <algorithm>
+#include <cstdio>
 
 #include "plb_collide.cuh"
 
@@ -370,7 +371,7 @@ __host__ __device__ constexpr int fused_smem_bytes(int depth)
 }
 #ifndef PLB_FUSED_DYN_SMEM
 #define PLB_FUSED_DYN_SMEM \
-    (PLB_FUSED_CARRY_SMEM || PLB_FUSED_STAGES * Q * PLB_FUSED_BLOCK * 16 > 48 * 1024 - 256)
+    (PLB_FUSED_CARRY_SMEM || PLB_FUSED_STAGES * 9 * PLB_FUSED_BLOCK * 16 > 48 * 1024 - 256)
 #endif
 
 // Resident CTAs per SM asked of ptxas, per collision model (PLB_FUSED_MINBLOCKS
@@ -1243,6 +1244,32 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
     PLB_LAUNCH_SMEM(COOP, (k_bulk_fused<C, F, D>), unsigned((warps + wpb - 1) / wpb),
                     PLB_FUSED_BLOCK, dyn_smem, st, a, deep, x_begin, x_end, strips,
                     rows_per_chunk, work_counter);
+}
+
+const char *kernel_build_info()
+{
+    static char text[320];
+    if (!text[0]) {
+        const char *ring = PLB_FUSED_STAGES < 2 ? "none"
+                           : PLB_FUSED_BULK     ? "tma-bulk"
+                                                : "cp.async";
+        snprintf(text, sizeof text,
+                 "bulk: block=%d ld_mode=%d st_mode=%d; fused: block=%d "
+                 "ctas_per_sm=%d/%d/%d (mrt/bgk/depth3) stages=%d ring=%s carry=%s "
+                 "smem=%s (%d / %d bytes per cta at depth 2 / 3)%s",
+                 PLB_BLOCK, PLB_LD_MODE, PLB_ST_MODE, PLB_FUSED_BLOCK,
+                 fused_min_blocks(2, 2), fused_min_blocks(0, 2), fused_min_blocks(2, 3),
+                 PLB_FUSED_STAGES, ring, PLB_FUSED_CARRY_SMEM ? "shared" : "registers",
+                 PLB_FUSED_DYN_SMEM ? "dynamic" : "static", fused_smem_bytes(2),
+                 fused_smem_bytes(3),
+#ifdef PLB_EMU_RUNTIME
+                 "; host emulation (test infrastructure)"
+#else
+                 ""
+#endif
+        );
+    }
+    return text;
 }
 
 int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,

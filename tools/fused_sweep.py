@@ -61,6 +61,7 @@ for collision, forcing in %(models)s:
         "kernel_share": round(kernel_ms / (ms * steps), 3),
         "pairs": info["pairs"], "rows": info["rows"]}
     p.close()
+out["build"] = capi.load_library().plb_build_info().decode().split("; ")[1]
 print(json.dumps(out))
 """
 
@@ -101,11 +102,12 @@ def main():
             print(f"{tag:44s} FAILED {proc.stderr[-300:]}", flush=True)
             continue
         res = json.loads(proc.stdout.strip().splitlines()[-1])
+        build = res.pop("build", "")
         cells = "  ".join(f"{k}: {v['glups']:6.2f} GLUPS (kernel share "
                           f"{v['kernel_share']}, pairs {v['pairs']}, rows {v['rows']}, "
                           f"rho hash {v['hash']})"
                           for k, v in res.items())
-        print(f"{tag:44s} {cells}", flush=True)
+        print(f"{tag:44s} {cells}  [{build}]", flush=True)
 
 
 if __name__ == "__main__":
