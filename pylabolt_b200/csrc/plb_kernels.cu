@@ -336,16 +336,18 @@ __host__ __device__ constexpr int fused_span(int depth) { return 64 - 2 * (depth
 #ifndef PLB_FUSED_STAGES
 #define PLB_FUSED_STAGES 2
 #endif
-// PLB_FUSED_BULK=1 (tuning variant, needs PLB_FUSED_STAGES >= 2): the ring is
-// filled by the TMA unit instead of per-lane cp.async -- a warp's row is nine
-// contiguous runs of 512 bytes, so one elected lane issues nine cp.async.bulk
-// copies that complete on a per-warp, per-slot mbarrier (no LSU instruction,
-// no address arithmetic in the other 31 lanes).
+// PLB_FUSED_BULK=1 (tuning variant): the ring is filled by the TMA unit instead
+// of per-lane cp.async -- a warp's row is nine contiguous runs of 512 bytes, so
+// one elected lane issues nine cp.async.bulk copies that complete on a
+// per-warp, per-slot mbarrier (no LSU instruction, no address arithmetic in
+// the other 31 lanes).  Here a slot is refilled right after it has been read
+// into registers, so PLB_FUSED_STAGES slots keep that many rows in flight and
+// a single slot (18 KB per CTA) already fetches one row ahead.
 #ifndef PLB_FUSED_BULK
 #define PLB_FUSED_BULK 0
 #endif
-#if PLB_FUSED_BULK && PLB_FUSED_STAGES < 2
-#error "PLB_FUSED_BULK needs a ring (PLB_FUSED_STAGES >= 2)"
+#if PLB_FUSED_BULK && PLB_FUSED_STAGES < 1
+#error "PLB_FUSED_BULK needs a ring (PLB_FUSED_STAGES >= 1)"
 #endif
 // PLB_FUSED_CARRY_SMEM=1 (tuning variant): the post-collision populations that
 // wait one or two iterations for their row (FusedCarry: 18 doubles per lane and
@@ -546,7 +548,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
     (void)carry_s;
     (void)ring_bar;
 #else
-#if PLB_FUSED_STAGES >= 2
+#if PLB_FUSED_STAGES >= 2 || PLB_FUSED_BULK
     __shared__ __align__(128) double2 ring[PLB_FUSED_STAGES][Q][PLB_FUSED_BLOCK];
 #endif
 #if PLB_FUSED_BULK
@@ -598,14 +600,14 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         const int n_rows = int(xe - xs) + 2 * LEVELS;
         const double *row0 = a.fin + L.at(xs - LEVELS, y);     // pair of row i = 0
 #if PLB_FUSED_BULK
-        constexpr int AHEAD = PLB_FUSED_STAGES - 1;
+        constexpr int AHEAD = PLB_FUSED_STAGES;
         // bytes of the warp's run that lie inside the padded row (the lanes
         // with in_row are a prefix of the warp), and the elected lane's view
         // of the run
         const unsigned run_bytes = 16u * unsigned(__popc(__ballot_sync(0xffffffffu, in_row)));
         const double *run0 = row0 - 2 * lane;
-        // row number j of this item into its slot; the slot was last read one
-        // iteration ago by every lane (__syncwarp: those reads are done)
+        // row number j of this item into its slot, which every lane has just
+        // read into registers (__syncwarp: those reads are done)
         auto fill = [&](int j) {
             __syncwarp();
             if (lane == 0 && run_bytes != 0 && j < n_rows) {
@@ -654,7 +656,6 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
             double fa[Q], fb[Q];
 #if PLB_FUSED_BULK
             {
-                fill(i + AHEAD);            // the slot read in the previous iteration
                 const unsigned g = filled + unsigned(i);
                 const int slot = int(g % PLB_FUSED_STAGES);
                 if (run_bytes != 0)         // row i has landed
@@ -666,6 +667,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
                     fa[k] = v.x;
                     fb[k] = v.y;
                 }
+                fill(i + AHEAD);            // the same slot, AHEAD rows on
             }
 #elif PLB_FUSED_STAGES >= 2
             {
@@ -1213,7 +1215,7 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
     static bool attributes_set = false;
     if (!attributes_set) {
         // the prefetch ring wants shared memory, nothing here wants L1
-        if (PLB_FUSED_STAGES >= 2 || PLB_FUSED_CARRY_SMEM)
+        if (PLB_FUSED_STAGES >= 2 || PLB_FUSED_BULK || PLB_FUSED_CARRY_SMEM)
             cudaFuncSetAttribute(k_bulk_fused<C, F, D>,
                                  cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
@@ -1250,9 +1252,9 @@ const char *kernel_build_info()
 {
     static char text[320];
     if (!text[0]) {
-        const char *ring = PLB_FUSED_STAGES < 2 ? "none"
-                           : PLB_FUSED_BULK     ? "tma-bulk"
-                                                : "cp.async";
+        const char *ring = PLB_FUSED_BULK         ? "tma-bulk"
+                           : PLB_FUSED_STAGES < 2 ? "none"
+                                                  : "cp.async";
         snprintf(text, sizeof text,
                  "bulk: block=%d ld_mode=%d st_mode=%d; fused: block=%d "
                  "ctas_per_sm=%d/%d/%d (mrt/bgk/depth3) stages=%d ring=%s carry=%s "

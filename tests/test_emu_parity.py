@@ -324,6 +324,9 @@ VARIANT_FLAGS = {
     # (everything in dynamic shared memory)
     "carry_bulk_s3": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1",
                       "-DPLB_FUSED_STAGES=3"],
+    # ... with a ring of one slot, refilled as soon as it has been read
+    "carry_bulk_s1": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1",
+                      "-DPLB_FUSED_STAGES=1"],
 }
 
 

@@ -44,6 +44,21 @@ VARIANTS = {
                            "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=8",
                            "-DPLB_FUSED_MINBLOCKS_D3=6"],
     "carry_mb3": ["-DPLB_FUSED_CARRY_SMEM=1"],
+    # ... and a TMA ring of ONE slot (refilled as soon as it has been read into
+    # registers: still one row ahead, 18 KB): 37 KB per CTA at depth 2, 55 KB at
+    # depth 3 -> five CTAs per SM (20 warps, 90 registers) / four (16 warps, 94
+    # registers); six CTAs (24 warps, the single-step kernel's occupancy) cost
+    # 8 bytes of spills at 80 registers
+    "cb_s1_mb5": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=1",
+                  "-DPLB_FUSED_MINBLOCKS=5", "-DPLB_FUSED_MINBLOCKS_D3=4"],
+    "cb_s1_mb6": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=1",
+                  "-DPLB_FUSED_MINBLOCKS=6", "-DPLB_FUSED_MINBLOCKS_D3=4"],
+    "cb_s1_mb4": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=1",
+                  "-DPLB_FUSED_MINBLOCKS=4", "-DPLB_FUSED_MINBLOCKS_D3=3"],
+    "cb_s1_b64_mb10": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=1",
+                       "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=10",
+                       "-DPLB_FUSED_MINBLOCKS_D3=8"],
+    "bulk_s1": ["-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=1"],
 }
 
 if __name__ == "__main__":

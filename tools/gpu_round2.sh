@@ -16,7 +16,11 @@ timeout 300 python -m pytest tests/test_gpu_fused.py tests/test_gpu_zz_fused_dep
 el "pytest fused: $(tail -1 $out/${tag}_pytest_fused.log)"
 # 2. two vs three steps per pass, occupancy / ring variants (each line ~7 s)
 timeout 120 python tools/fused_sweep.py $L/libplb.so:PLB_FUSE=0 $L/libplb.so $L/libplb.so:PLB_FUSE_DEPTH=3 > $out/${tag}_sweep.txt 2>&1
-timeout 600 python tools/fused_sweep.py --models mrt \
+timeout 720 python tools/fused_sweep.py --models mrt \
+    $V/libplb_cb_s1_mb5.so $V/libplb_cb_s1_mb6.so $V/libplb_cb_s1_mb4.so $V/libplb_cb_s1_b64_mb10.so \
+    $V/libplb_cb_s1_mb5.so:PLB_FUSE_DEPTH=3 $V/libplb_cb_s1_mb5.so:PLB_FUSE_DEPTH=3,PLB_FUSED_ROWS=64 \
+    $V/libplb_cb_s1_b64_mb10.so:PLB_FUSE_DEPTH=3 $V/libplb_cb_s1_mb5.so:PLB_FUSED_ROWS=64 \
+    $V/libplb_cb_s1_mb5.so:PLB_FUSED_DYNAMIC=1,PLB_FUSED_ROWS=128 $V/libplb_bulk_s1.so \
     $L/libplb.so:PLB_FUSE_DEPTH=3,PLB_FUSED_ROWS=16 $L/libplb.so:PLB_FUSE_DEPTH=3,PLB_FUSED_ROWS=64 \
     $V/libplb_d3_b64_mb5.so:PLB_FUSE_DEPTH=3 $V/libplb_d3_s3_b64_mb5.so:PLB_FUSE_DEPTH=3 \
     $V/libplb_d3_mb3.so:PLB_FUSE_DEPTH=3 \
