@@ -616,8 +616,13 @@ int step_fused(plb_solver *s, int depth)
     // level 0 reads `depth - 1` rows either side of the rows it delivers and
     // the lattice has one ghost row: columns closer than depth - 2 to the slab
     // edge are left out (they cannot be deep enough anyway)
+    // A persistent grid (PLB_FUSED_DYNAMIC) holds every CTA slot until the pass is
+    // over, so the later list passes of this group -- and with them the steps
+    // the neighbour ranks are waiting for -- would queue up behind it instead
+    // of running beside it: between ranks the grid is always the plain one.
+    unsigned *work_counter = s->comm ? nullptr : s->work_counter;
     s->launches += launch_bulk_fused(a, s->deep_dev, depth, depth - 2, L.nx - (depth - 2),
-                                     s->fused_rows, s->work_counter, s->stream);
+                                     s->fused_rows, work_counter, s->stream);
     if (prof) {
         CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used + 1], s->stream));
         s->prof_used += 2;
