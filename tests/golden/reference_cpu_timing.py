@@ -2,9 +2,10 @@
 """Times the REFERENCE's own CPU path (numba kernels, Solver.single_time_step)
 next to the oracle port that bench.py's cpu_baseline / --impl reference use,
 on the same case and thread count -- in a container that holds the reference
-checkout (the GPU box does not, which is why the bench times the port).
+checkout (the GPU box does not, which is why the bench times the port).  Test
+infrastructure, like make_golden.py next to it: it checks the checker.
 
-    python tools/reference_cpu_timing.py [--n 1024] [--steps 10] [--threads 8]
+    python tests/golden/reference_cpu_timing.py [--n 1024] [--steps 10] [--threads 8]
         > profiles/<round>_cpu_reference_vs_port.json
 
 The point: the port is a fair stand-in -- it is not slower than the code it
@@ -21,10 +22,11 @@ import sys
 import tempfile
 import time
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
-sys.path.insert(0, os.path.join(REPO, "tests", "golden"))
+sys.path.insert(0, HERE)
 
 
 def build_reference(n, steps, threads):
