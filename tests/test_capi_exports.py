@@ -57,3 +57,14 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(root, name)).read()
                 assert "import oracle" not in text and "from oracle" not in text
                 assert "liboracle" not in text
+
+
+def test_build_info_describes_the_shipped_kernels():
+    """plb_build_info needs no device: the shipped libraries are the measured
+    configuration (cp.async ring of two rows, carry in registers, three CTAs
+    per SM), production and strict alike."""
+    for strict in (False, True):
+        text = capi.load_library(strict=strict).plb_build_info().decode()
+        assert "fused: block=128 ctas_per_sm=3/3/2" in text, text
+        assert "stages=2 ring=cp.async carry=registers smem=static" in text, text
+        assert "emulation" not in text
