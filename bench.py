@@ -295,7 +295,7 @@ def run_reference(args, rank, world, text, scaling):
     if rank != 0:
         return
     base = time_cpu_port(args.workload, args.steps, args.warmup,
-                         budget_s=90.0, sample=4096)
+                         budget_s=90.0, sample=args.cpu_sample)
     line = {
         "impl": "reference", "metric": "fluidLB D2Q9 fp64 lattice updates",
         "value": base["value"], "unit": "GLUPS", "n_gpus": args.gpus,
@@ -483,6 +483,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0,
                     help="shrink the lattice (debugging only; a scaled run is "
                          "not a benchmark value)")
+    ap.add_argument("--cpu-sample", type=int, default=4096,
+                    help="edge of the square lattice the CPU arm is timed on "
+                         "(smaller: contract tests only)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -521,7 +524,8 @@ def main():
             "roofline": cav["roofline"], "e2e": cav["e2e"]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = time_cpu_port(args.workload, 200, 2, budget_s=15.0, sample=4096)
+        cpu = time_cpu_port(args.workload, 200, 2, budget_s=15.0,
+                            sample=args.cpu_sample)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
         line = {
