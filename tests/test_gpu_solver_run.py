@@ -11,7 +11,7 @@ from pylabolt_b200 import capi
 from pylabolt_b200.comm import SingleComm
 from pylabolt_b200.io_operator import strip_ghost
 from pylabolt_b200.solver import Solver
-from test_gpu_parity import make_solver, oracle_for, rel_err
+from test_gpu_parity import make_solver, oracle_for
 
 pytestmark = pytest.mark.gpu
 

@@ -2,7 +2,6 @@
 """Host <-> device transfer rates on this box (development tool): torch pinned
 copies as the ceiling, then plb_upload / plb_download of rho and u."""
 import os, sys, time
-import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import torch
