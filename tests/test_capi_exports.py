@@ -68,3 +68,20 @@ def test_build_info_describes_the_shipped_kernels():
         assert "fused: block=128 ctas_per_sm=3/3/2" in text, text
         assert "stages=2 ring=cp.async carry=registers smem=static" in text, text
         assert "emulation" not in text
+
+
+def test_create_fails_loudly_without_a_device():
+    """No GPU here: plb_create must return an error code with a message (and
+    the Python shim must raise), never hand back a handle that computes
+    somewhere else."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(capi.PlbError, match="libplb error"):
+        capi.Plb(16, 16, 1.25)
+    lib = capi.load_library(strict=False)
+    handle = ctypes.c_void_p()
+    cfg = capi.PlbConfig()
+    rc = lib.plb_create(ctypes.byref(cfg), ctypes.byref(handle))
+    assert rc < 0 and not handle.value
+    assert lib.plb_last_error().decode() != ""
