@@ -74,8 +74,9 @@ def test_create_fails_loudly_without_a_device():
     """No GPU here: plb_create must return an error code with a message (and
     the Python shim must raise), never hand back a handle that computes
     somewhere else."""
-    import torch
-    if torch.cuda.is_available():
+    # (not asked of torch: importing it here would put the real CUDA runtime
+    # into this process's global symbol scope)
+    if os.path.exists("/dev/nvidiactl"):
         pytest.skip("a CUDA device is present")
     with pytest.raises(capi.PlbError, match="libplb error"):
         capi.Plb(16, 16, 1.25)
