@@ -191,7 +191,7 @@ class Oracle:
 
     def residues(self):
         """utils/residues.py:199-222 -> (res_density, res_ux, res_uy)."""
-        s = self.residue_sums()
+        s = self.last_residue_sums = self.residue_sums()
         eps = self.params.float_min
         return (np.sqrt(s[0] / (s[1] + eps)), np.sqrt(s[2] / (s[3] + eps)),
                 np.sqrt(s[4] / (s[5] + eps)))

@@ -29,7 +29,10 @@ Shims (none changes arithmetic):
 
 Each fixture <case>.npz stores: flags and ids after setup, every boundary
 element's link list, initial rho/u, and rho / u / pop_new (padded reference
-layouts) after the recorded step counts.  Fixtures are small (a few 100 KB).
+layouts) after the recorded step counts, the wall / body forces of the
+reference's force kernels, and the residue sums + residues of the reference's
+residue operator called at exactly the recorded steps (field_old = 0 before
+the first).  Fixtures are small (a few 100 KB).
 """
 import contextlib
 import importlib.metadata
@@ -210,6 +213,38 @@ def reference_forces(solver):
     return wall, body
 
 
+def reference_residues(solver, time_step):
+    """The reference's own residue operator (utils/residues.py:171-222 with
+    the numba kernels of cpu/compute_residues_kernels.py:6-73) at a recorded
+    step: returns the raw sums it reduces -- (num, den) of density and
+    (num_x, den_x, num_y, den_y) of velocity -- and the residues it logs.
+    field_old of the operator lives on between calls (zeros before the first
+    one), exactly as in Solver.run with std_out_interval = the recorded
+    steps."""
+    st = solver.state
+    op = solver.residue_operator
+    seen = []
+    real_reduce = solver.mpi_operator.reduce
+
+    def reduce(local_array, operation="sum"):
+        seen.append(np.array(local_array, dtype=np.float64))
+        return real_reduce(local_array, operation=operation)
+    keep = st.control.std_out_interval
+    st.control.std_out_interval = 1
+    solver.mpi_operator.reduce = reduce
+    try:
+        op.compute_residues(st, solver.backend, solver.mpi_operator, time_step)
+    finally:
+        solver.mpi_operator.reduce = real_reduce
+        st.control.std_out_interval = keep
+    order = list(op.fields_list)
+    sums = np.concatenate([seen[order.index("density")],
+                           seen[order.index("velocity")]])
+    res = np.concatenate([op.residues["res_density"],
+                          op.residues["res_velocity"]])
+    return sums, np.asarray(res, np.float64)
+
+
 def generate(case_name, factory, kwargs, record_steps, comm, out_dir):
     simulation = factory(**kwargs)
     cwd = os.getcwd()
@@ -241,6 +276,8 @@ def generate(case_name, factory, kwargs, record_steps, comm, out_dir):
                     data[f"density_{step}"] = fields.density.copy()
                     data[f"velocity_{step}"] = fields.velocity.copy()
                     data[f"pop_{step}"] = fields.pop_fluid_new.copy()
+                    data[f"residue_sums_{step}"], data[f"residues_{step}"] = \
+                        reference_residues(solver, step)
             data["record_steps"] = np.asarray(record_steps, np.int64)
         finally:
             os.chdir(cwd)

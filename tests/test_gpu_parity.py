@@ -185,6 +185,33 @@ def test_residues_match_oracle():
         s.close()
 
 
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN_CASES))
+def test_residues_match_the_reference_operator(golden_dir, name):
+    """plb_residue_sums / ResidueOperator against the REFERENCE's residue
+    operator run at the recorded steps (tests/golden/make_golden.py:
+    reference_residues; utils/residues.py:171-222,
+    cpu/compute_residues_kernels.py:6-73).  Both sides sum in an order of
+    their own, so rounding-level tolerance on the sums; the strict build's
+    fields are bit-equal to the reference's, so nothing else differs."""
+    factory, kwargs, record = cases.GOLDEN_CASES[name]
+    data = np.load(os.path.join(golden_dir, name + ".npz"))
+    s = make_solver(factory(**kwargs), strict=True)
+    try:
+        done = 0
+        for step in record:
+            s.advance(step - done, store_moments_last=True)
+            done = step
+            got = s.plb.residue_sums()
+            want = data[f"residue_sums_{step}"]
+            assert np.allclose(got, want, rtol=1e-12, atol=1e-300), step
+            eps = s.state.control.float_min
+            res = np.sqrt(got[0::2] / (got[1::2] + eps))
+            assert np.allclose(res, data[f"residues_{step}"], rtol=1e-12,
+                               atol=1e-300), step
+    finally:
+        s.close()
+
+
 def test_mass_is_conserved_in_closed_periodic_box():
     """Size-independent property: no walls, no forcing -> sum(rho) constant."""
     sim = cases.periodic_box(96, 64, forcing=None)

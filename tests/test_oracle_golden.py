@@ -41,6 +41,29 @@ def test_oracle_matches_reference_bit_for_bit(golden_dir, name):
         assert np.array_equal(orc.pop_new, data[f"pop_{step}"]), step
 
 
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN_CASES))
+def test_oracle_residues_match_the_reference_operator(golden_dir, name):
+    """oracle_residue_sums against the reference's own ResidueOperator
+    (utils/residues.py:171-222 + cpu/compute_residues_kernels.py:6-73) called
+    at the recorded steps: the six sums it reduces and the three residues it
+    logs.  The reference sums with a numba prange reduction whose order is
+    not fixed, hence a rounding-level tolerance instead of bit equality."""
+    factory, kwargs, record = cases.GOLDEN_CASES[name]
+    data = load_golden(golden_dir, name)
+    orc = oracle_from_golden(data, factory(**kwargs), n_threads=2)
+    orc.initialize_pop()
+    done = 0
+    for step in record:
+        orc.step(step - done)
+        done = step
+        res = orc.residues()
+        sums = orc.last_residue_sums
+        assert np.allclose(sums, data[f"residue_sums_{step}"], rtol=1e-12,
+                           atol=1e-300), step
+        assert np.allclose(res, data[f"residues_{step}"], rtol=1e-12,
+                           atol=1e-300), step
+
+
 def test_lattice_constants_match_reference(golden_dir):
     """base/lattice.py:41-60 values, as probed from the reference."""
     from oracle.oracle import lattice_constants
