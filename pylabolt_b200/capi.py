@@ -60,9 +60,16 @@ class PlbError(RuntimeError):
 
 _libs = {}
 
+# The product only ever runs the sm_100a build.  tests/emu/ holds a host
+# emulation of the same sources (kernel-logic tests without a GPU); its test
+# harness -- tests/conftest.py, never the product -- flips this switch.  With
+# it off, a PLB_LIB that points at an emulated build is refused.
+_accept_emulated_build = False
+
 
 def load_library(strict=None):
-    """dlopen libplb.so (or libplb_strict.so when strict / PLB_STRICT=1)."""
+    """dlopen libplb.so (or libplb_strict.so when strict / PLB_STRICT=1).
+    PLB_LIB selects another sm_100a build of libplb (tuning variants)."""
     if strict is None:
         strict = os.environ.get("PLB_STRICT", "0") not in ("", "0")
     strict = bool(strict)
@@ -112,6 +119,11 @@ def load_library(strict=None):
     lib.plb_build_info.argtypes = []
     lib.plb_build_info.restype = ctypes.c_char_p
     lib.plb_device_pci_bus_id.argtypes = [i32, ctypes.c_char_p, i32]
+    info = (lib.plb_build_info() or b"").decode()
+    if "emulation" in info and not _accept_emulated_build:
+        raise PlbError(
+            f"{path} is a host emulation of libplb (test infrastructure): "
+            "the b200 back end has no CPU path and will not load it.")
     _libs[path] = lib
     return lib
 

@@ -31,6 +31,9 @@ class SingleComm:
     def Allreduce(self, local, out, op="sum"):
         out[...] = local
 
+    def all_agree(self, flag):
+        return bool(flag)
+
     def bcast_bytes(self, data, root=0):
         return data
 
@@ -64,8 +67,25 @@ class TorchComm:
         self.dist.barrier()
 
     def Abort(self, code=1):
-        """Configuration errors are raised on every rank (all ranks parse the
-        same case file), so the job ends without a collective teardown."""
+        """MPI_Abort semantics (the reference calls comm.Abort() on every
+        fatal error): the calling rank leaves at once with a non-zero status,
+        without waiting in any collective; torchrun then terminates the other
+        ranks, and a peer that is already spinning on this rank's slab face
+        gives up after PLB_P2P_TIMEOUT_S.  A rank-local failure (a missing
+        device, overlapping obstacles seen by one slab only) therefore ends
+        the job instead of hanging it."""
+        import sys
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if self.Get_size() > 1:
+            os._exit(code if code else 1)
+
+    def all_agree(self, flag):
+        """True on every rank iff `flag` is true on every rank."""
+        mine = np.array([1.0 if flag else 0.0])
+        out = np.zeros_like(mine)
+        self.Allreduce(mine, out, op="min")
+        return bool(out[0] > 0.5)
 
     def Allreduce(self, local, out, op="sum"):
         t = self.torch.as_tensor(np.ascontiguousarray(local)).to(self.device)

@@ -760,6 +760,23 @@ int setup_p2p(plb_solver *s)
     return PLB_OK;
 }
 
+// Peer-to-peer faces: has a slab-face wait of this rank timed out?  Called by
+// every entry point that hands device results to the host, after it has
+// synchronised the stream -- a neighbour rank that stalled makes later steps
+// run on stale face buffers, so nothing computed since may leave the library
+// looking like a result.
+int check_faces(plb_solver *s)
+{
+    if (!s->p2p || !s->xbuf) return PLB_OK;
+    unsigned long long status = 0;
+    CUDA_TRY(cudaMemcpy(&status, s->xbuf + 2 * sizeof status, sizeof status,
+                        cudaMemcpyDeviceToHost));
+    if (status)
+        return fail(PLB_ERR_NCCL, "slab-face exchange timed out: a neighbour "
+                    "rank never published its step (PLB_P2P_TIMEOUT_S)");
+    return PLB_OK;
+}
+
 void close_p2p(plb_solver *s)
 {
     if (s->peer_left) cudaIpcCloseMemHandle(s->peer_left);
@@ -1276,6 +1293,7 @@ int plb_download(plb_handle s, int32_t field, void *host, size_t bytes)
     const size_t size = size_t((L.nx + 2) * (L.ny + 2));
     const size_t inner = size_t(L.nx * L.ny);
     double *out = static_cast<double *>(host);
+    auto checked = [&](int rc) { return rc ? rc : check_faces(s); };
     switch (field) {
     case PLB_SOLID:
         if (bytes != size) return fail(PLB_ERR_INVALID, "PLB_SOLID expects %zu bytes", size);
@@ -1283,19 +1301,19 @@ int plb_download(plb_handle s, int32_t field, void *host, size_t bytes)
         return PLB_OK;
     case PLB_DENSITY:
         if (bytes != size * 8) return fail(PLB_ERR_INVALID, "PLB_DENSITY expects %zu bytes", size * 8);
-        return download_padded(s, out, 1, s->rho(), L.plane, 0);
+        return checked(download_padded(s, out, 1, s->rho(), L.plane, 0));
     case PLB_VELOCITY:
         if (bytes != size * 16) return fail(PLB_ERR_INVALID, "PLB_VELOCITY expects %zu bytes", size * 16);
-        return download_padded(s, out, 2, s->ux(), L.plane, 0);
+        return checked(download_padded(s, out, 2, s->ux(), L.plane, 0));
     case PLB_POP:
         if (bytes != size * 72) return fail(PLB_ERR_INVALID, "PLB_POP expects %zu bytes", size * 72);
-        return download_padded(s, out, Q, s->f[s->cur], L.plane, 1);
+        return checked(download_padded(s, out, Q, s->f[s->cur], L.plane, 1));
     case PLB_DENSITY_INNER:
         if (bytes != inner * 8) return fail(PLB_ERR_INVALID, "PLB_DENSITY_INNER expects %zu bytes", inner * 8);
-        return download_inner(s, out, 1, s->rho(), L.plane);
+        return checked(download_inner(s, out, 1, s->rho(), L.plane));
     case PLB_VELOCITY_INNER:
         if (bytes != inner * 16) return fail(PLB_ERR_INVALID, "PLB_VELOCITY_INNER expects %zu bytes", inner * 16);
-        return download_inner(s, out, 2, s->ux(), L.plane);
+        return checked(download_inner(s, out, 2, s->ux(), L.plane));
     default:
         return fail(PLB_ERR_INVALID, "field %d cannot be downloaded", field);
     }
@@ -1377,7 +1395,7 @@ int plb_download_link_exchange(plb_handle s, double *out, int64_t n_values)
     CUDA_TRY(cudaMemcpyAsync(out, s->exch_dev, size_t(n_values) * sizeof(double),
                              cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return PLB_OK;
+    return check_faces(s);
 }
 
 int plb_sync(plb_handle s)
@@ -1387,15 +1405,7 @@ int plb_sync(plb_handle s)
     if (int rc = flush_pending(s)) return rc;
     CUDA_TRY(cudaStreamSynchronize(s->edge_stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    if (s->p2p) {
-        unsigned long long status = 0;
-        CUDA_TRY(cudaMemcpy(&status, s->xbuf + 2 * sizeof status, sizeof status,
-                            cudaMemcpyDeviceToHost));
-        if (status)
-            return fail(PLB_ERR_NCCL, "slab-face exchange timed out: a neighbour "
-                        "rank never published its step (PLB_P2P_TIMEOUT_S)");
-    }
-    return PLB_OK;
+    return check_faces(s);
 }
 
 int plb_residue_sums(plb_handle s, double out[6])
@@ -1418,7 +1428,7 @@ int plb_residue_sums(plb_handle s, double out[6])
     CUDA_TRY(cudaMemcpyAsync(out, s->res_out, 6 * sizeof(double), cudaMemcpyDeviceToHost,
                              s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return PLB_OK;
+    return check_faces(s);
 }
 
 int plb_comm_unique_id(void *id128)

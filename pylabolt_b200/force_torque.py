@@ -22,9 +22,11 @@ _INV = np.array([0, 3, 4, 1, 2, 7, 8, 5, 6], dtype=np.int64)
 
 
 class MomentumExchange:
-    def __init__(self, state, link_inds):
+    def __init__(self, state, link_inds, every_element=False):
         """``link_inds``: padded flat indices of libplb's link nodes, in list
-        order (plb_link_nodes)."""
+        order (plb_link_nodes).  ``every_element``: also reduce the elements
+        that are not walls (the reference's kernel can be called on any
+        element; its operator only calls it on walls) -- parity tests."""
         self.state = state
         self.link_inds = np.asarray(link_inds, dtype=np.int64)
         self.n_links = self.link_inds.shape[0]
@@ -45,7 +47,11 @@ class MomentumExchange:
         # walls: three links per node of every boundary element
         self.wall_terms = []
         for el in state.boundary.boundary_elements:
-            nodes = el.boundary_nodes[~f.solid[el.boundary_nodes]]
+            # only wall elements are reduced (boundary_operator.py:224-230);
+            # the rows of inlets / outlets / periodic pairs stay zero
+            nodes = (el.boundary_nodes[~f.solid[el.boundary_nodes]]
+                     if (el.wall or every_element)
+                     else np.zeros(0, dtype=np.int64))
             rows = rows_of(nodes)
             rows = rows[rows >= 0]
             out = np.asarray(el.out_list, dtype=np.int64)

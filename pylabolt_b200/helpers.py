@@ -33,24 +33,33 @@ def load_simulation(comm, mpi_rank):
         raise
 
 
+def _format_residue(value):
+    """One logged quantity: a scalar, a one-component array or a vector."""
+    parts = np.atleast_1d(np.asarray(value, dtype=np.float64)).ravel()
+    shown = ["%.5e" % v for v in parts]
+    return shown[0] if len(shown) == 1 else "(" + ", ".join(shown) + ")"
+
+
 class SimulationStatusLogger:
-    """``time | res_density | res_velocity`` line every std_out_interval steps
-    (pylabolt/utils/helpers.py:29-56)."""
+    """The status line of the reference (pylabolt/utils/helpers.py:29-56):
+    ``time: <step> | <name>: <value> | ...`` on rank 0, on the steps that are
+    multiples of ``control.std_out_interval``.  The column widths are part of
+    the output contract (log scrapers split on them)."""
+
+    TIME_LABEL = "%-5s %-10d"
+    FIELD = "%-5s: %s"
 
     def __init__(self, mpi_rank, verbose=True):
         self.verbose = verbose
 
+    def due(self, state, time_step):
+        every = state.control.std_out_interval
+        return every is not None and time_step % every == 0
+
     def log_data(self, state, time_step, **values):
-        interval = state.control.std_out_interval
-        if interval is None or time_step % interval != 0:
+        if not self.due(state, time_step):
             return
-        parts = [f"{'time:':<5} {time_step:<10}"]
-        for key, value in values.items():
-            if np.isscalar(value):
-                text = f"{value:.5e}"
-            elif len(value) == 1:
-                text = f"{value[0]:.5e}"
-            else:
-                text = "(" + ", ".join(f"{v:.5e}" for v in value) + ")"
-            parts.append(f"{key:<5}: {text}")
-        print_log(" | ".join(parts), state.domain.mpi_rank, self.verbose)
+        line = [self.TIME_LABEL % ("time:", time_step)]
+        line += [self.FIELD % (name, _format_residue(value))
+                 for name, value in values.items()]
+        print_log(" | ".join(line), state.domain.mpi_rank, self.verbose)

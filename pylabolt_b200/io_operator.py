@@ -101,6 +101,10 @@ class InputOutputOperator:
     def _history_path(self, name):
         return os.path.join(self.root_dir, "output", "histories", name + ".dat")
 
+    def _keep_history(self, name):
+        return (getattr(self, "_histories_resume", False) and
+                os.path.exists(self._history_path(name)))
+
     def setup_write_histories(self, state):
         """Headers of output/histories/<name>.dat, one file per obstacle and
         per wall boundary element, written by rank 0."""
@@ -113,6 +117,8 @@ class InputOutputOperator:
                     exist_ok=True)
         if state.obstacle.write_obstacle_data:
             for body in state.obstacle.obstacles:
+                if self._keep_history(body.name):
+                    continue
                 with open(self._history_path(body.name), "w") as out:
                     out.write(f"{'#':5} {'PyLaBolt obstacle history'}\n"
                               f"{'#':5} {'ID':8}: {body.id}\n"
@@ -125,7 +131,7 @@ class InputOutputOperator:
                          "force_x", "force_y", "torque")) + "\n")
         if state.boundary.write_boundary_data:
             for element in state.boundary.boundary_elements:
-                if not element.wall:
+                if not element.wall or self._keep_history(element.name):
                     continue
                 with open(self._history_path(element.name), "w") as out:
                     out.write(f"{'#':5} {'PyLaBolt boundary history'}\n"
@@ -180,6 +186,15 @@ class InputOutputOperator:
         np.savez(path, pop_fluid_new=self.plb.download(capi.POP),
                  time_step=np.int64(time_step),
                  shape=np.asarray(state.domain.shape, dtype=np.int64))
+
+    def has_checkpoint(self, state, time_step):
+        return bool(time_step) and os.path.exists(
+            self._checkpoint_path(state, time_step))
+
+    def resume_histories(self, state):
+        """A restarted run continues the history files of the run it resumes
+        (rows are appended; headers only for files that do not exist yet)."""
+        self._histories_resume = True
 
     def load_checkpoint(self, state, time_step):
         """start_time > 0 resumes from the checkpoint of that step, if one

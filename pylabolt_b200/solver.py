@@ -240,12 +240,33 @@ class Solver:
         rank = st.domain.mpi_rank
         print_log("\n" + "-" * 80, rank, verbose)
         print_log("Running simulation...\n", rank, verbose)
-        if not self.io_operator.load_checkpoint(st, st.control.start_time):
+        # Restart (start_time > 0 with a checkpoint of that step): a decision
+        # of the whole job -- a rank whose file is missing must not quietly
+        # begin from f_eq while its neighbours resume.
+        found = self.io_operator.has_checkpoint(st, st.control.start_time)
+        resumed = self.comm.all_agree(found)
+        if found and not resumed:
+            print_log("-" * 80, rank, True)
+            print_log("FATAL ERROR!", rank, True)
+            print_log("checkpoint of step " + str(st.control.start_time) +
+                      " is missing on at least one rank", rank, True)
+            self.comm.Abort()
+            raise RuntimeError("checkpoint missing on a neighbouring rank")
+        if resumed:
+            # The populations of step start_time come back; that step's
+            # fields, histories and forces were written by the run that made
+            # the checkpoint (rho / u on the device still hold the case
+            # file's initial fields until the next output step), so nothing
+            # is written for it again and the history files are continued.
+            self.io_operator.load_checkpoint(st, st.control.start_time)
+            self.io_operator.resume_histories(st)
+        else:
             self.plb.initialize_pop()
-        if self.momentum is not None:
-            self.compute_forces(self.momentum.initial_exchange(st.lattice))
-        self.io_operator.write_fields(st, self.backend, st.control.start_time)
-        self.io_operator.write_histories(st, time_step=0)
+            if self.momentum is not None:
+                self.compute_forces(self.momentum.initial_exchange(st.lattice))
+            self.io_operator.write_fields(st, self.backend,
+                                          st.control.start_time)
+            self.io_operator.write_histories(st, time_step=0)
         run_time_start = time.perf_counter()
         for time_step in range(st.control.start_time + 1,
                                st.control.end_time + 1):
@@ -267,6 +288,11 @@ class Solver:
             self.io_operator.write_fields(st, self.backend, time_step)
             self.io_operator.write_histories(st, time_step)
             self.io_operator.write_checkpoint(st, time_step)
+            if moments or links:
+                # data left the device on this step: a slab-face time-out
+                # (dead neighbour rank) must stop the run here, not after
+                # the last step
+                self.plb.sync()
         self.plb.sync()
         run_time = time.perf_counter() - run_time_start
         print_log("\n" + "-" * 80, rank, verbose)

@@ -29,6 +29,10 @@ for p in (REPO, TESTS):
         sys.path.insert(0, p)
 
 
+from pylabolt_b200 import capi  # noqa: E402
+capi._accept_emulated_build = True      # this worker IS the emulation harness
+
+
 class ThreadWorld:
     def __init__(self, size):
         self.size = size

@@ -25,7 +25,11 @@ def run_bench(*args, emulated=True):
     env = dict(os.environ)
     if emulated:
         env["PLB_LIB"] = build_emu.build()
-    proc = subprocess.run([sys.executable, os.path.join(REPO, "bench.py")] + list(args),
+    # bench.py itself only loads sm_100a builds; the emulated arm goes through
+    # the harness wrapper, which flips the loader's test-only switch first
+    head = ([os.path.join(HERE, "emu", "run_emulated.py")] if emulated else [])
+    proc = subprocess.run([sys.executable] + head +
+                          [os.path.join(REPO, "bench.py")] + list(args),
                           env=env, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stderr[-2000:]
     lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]

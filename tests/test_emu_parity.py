@@ -39,6 +39,7 @@ def emu(emu_lib, monkeypatch):
     """Routes THIS TEST's solvers to the emulated library (PLB_LIB is the
     loader's explicit override; the product default never points here)."""
     monkeypatch.setenv("PLB_LIB", emu_lib)
+    monkeypatch.setattr(capi, "_accept_emulated_build", True)
     monkeypatch.delenv("PLB_FUSED_ROWS", raising=False)
     monkeypatch.delenv("PLB_FUSE_DEPTH", raising=False)
     monkeypatch.delenv("PLB_EMU_BLOCK_ORDER", raising=False)

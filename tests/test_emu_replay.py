@@ -28,7 +28,7 @@ ORACLE = ("(against_oracle and (cavity_101 or wide_row or odd_sizes or "
 def test_solver_life_cycle_on_the_emulator(depth, guard, select):
     lib = build_emu.build()
     env = dict(os.environ, PLB_LIB=lib, PLB_FUSE="2", PLB_FUSE_DEPTH=depth,
-               PLB_EMU_GUARD=guard)
+               PLB_EMU_GUARD=guard, PLB_EMU_TESTING="1")
     proc = subprocess.run(
         [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
          os.path.join(HERE, "test_gpu_solver_run.py"),

@@ -68,7 +68,7 @@ def test_host_reduction_matches_reference_kernels(golden_dir, name):
     arrays (what the link kernel records on the device)."""
     data, record, orc, st = setup(golden_dir, name)
     fluid = np.flatnonzero(~st.fields.solid & ~st.fields.ghost_node)
-    mom = MomentumExchange(st, fluid)
+    mom = MomentumExchange(st, fluid, every_element=True)   # kernel-level parity
 
     def exchange():
         return orc.pop[fluid][:, 1:] + orc.pop_new[fluid][:, _INV[1:]]

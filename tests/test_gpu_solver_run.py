@@ -67,9 +67,18 @@ def test_forces_match_reference_kernels(golden_dir, name):
     sim.obstacle_dict["options"] = dict(sim.obstacle_dict["options"],
                                         compute_force_torque=True)
     s = make_solver(sim, strict=True)
-    # periodic elements own no links (the reference only evaluates wall ones)
-    real = [n for n, el in enumerate(s.state.boundary.boundary_elements)
-            if el.type_fluid != "periodic"]
+    # periodic elements own no links.  The golden forces come from the
+    # reference's KERNEL called on every element; its operator (and ours)
+    # only fills the rows of wall elements (boundary_operator.py:224-230).
+    from pylabolt_b200.force_torque import MomentumExchange
+    elements = s.state.boundary.boundary_elements
+    real = [n for n, el in enumerate(elements) if el.type_fluid != "periodic"]
+    not_wall = [n for n, el in enumerate(elements) if not el.wall]
+    s.compute_forces(s.momentum.initial_exchange(s.state.lattice))
+    assert not s.state.boundary.global_force[not_wall].any()
+    assert not s.state.boundary.local_force[not_wall].any()
+    s.momentum = MomentumExchange(s.state, s.plb.link_nodes(),
+                                  every_element=True)
     try:
         wall, body = s.compute_forces(s.momentum.initial_exchange(s.state.lattice))
         assert np.abs(wall[real] - data["wall_force_0"][real]).max(initial=0) <= 1e-12
@@ -91,21 +100,41 @@ def test_forces_match_reference_kernels(golden_dir, name):
 
 
 def test_checkpoint_restart_is_bit_identical(tmp_path, monkeypatch):
-    monkeypatch.chdir(tmp_path)
-
+    """A run split at a checkpoint leaves the same populations, the same
+    output/fields files and the same history rows as the uninterrupted run:
+    the restart neither rewrites t_<start>.npz with the case file's initial
+    fields nor truncates the histories."""
     def solver(start, end, ckpt):
         sim = cases.periodic_box(end_time=end)
         sim.control_dict["start_time"] = start
         sim.control_dict["checkpoint_interval"] = ckpt
+        sim.control_dict["save_interval"] = 5
+        sim.obstacle_dict["options"] = dict(
+            sim.obstacle_dict["options"], compute_force_torque=True,
+            write_obstacle_data={"interval": 5})
         s = Solver(SingleComm(), "b200", simulation=sim, verbose=False)
         s.set_backend()
         s.compile()
         return s
 
+    def outputs():
+        fields = {name: dict(np.load(os.path.join("output/fields", name)))
+                  for name in sorted(os.listdir("output/fields"))}
+        hist = {name: open(os.path.join("output/histories", name)).read()
+                for name in sorted(os.listdir("output/histories"))}
+        return fields, hist
+
+    (tmp_path / "whole").mkdir()
+    monkeypatch.chdir(tmp_path / "whole")
     whole = solver(0, 30, None)
     whole.run()
     want = whole.plb.download(capi.POP)
     whole.close()
+    want_fields, want_hist = outputs()
+    assert "t_15.npz" in want_fields and want_hist
+
+    (tmp_path / "split").mkdir()
+    monkeypatch.chdir(tmp_path / "split")
     first = solver(0, 15, 15)
     first.run()
     first.close()
@@ -115,6 +144,12 @@ def test_checkpoint_restart_is_bit_identical(tmp_path, monkeypatch):
     got = second.plb.download(capi.POP)
     second.close()
     assert np.array_equal(got, want)
+    got_fields, got_hist = outputs()
+    assert sorted(got_fields) == sorted(want_fields)
+    for name, arrays in want_fields.items():
+        for key, value in arrays.items():
+            assert np.array_equal(got_fields[name][key], value), (name, key)
+    assert got_hist == want_hist
 
 
 def test_pop_upload_download_round_trip():
