@@ -65,14 +65,26 @@ def test_own_arm_line():
     assert roof["bound"] == "hbm" and roof["unit"] == "GB/s"
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
     # nine steps = four two-step passes + one single step, all counted
-    assert roof["pairs"] == 4 and roof["single_steps"] == 1 and roof["triples"] == 0
+    reps = line["repeats"]
+    assert reps >= 1 and len(line["repeat_ms"]) == reps
+    assert roof["pairs"] == 4 * reps and roof["single_steps"] == reps and roof["triples"] == 0
+    assert roof["frac"] <= roof["step_equivalent_frac"]
     assert "fused: block=" in roof["kernel_build"]
     assert line["gpu_launches"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["e2e"]["value"] != line["value"]
-    assert abs(line["e2e"]["mean_density_check"] - 1.0) < 1e-9     # mass is conserved
+    assert abs(line["e2e"]["global_mean_density"] - 1.0) < 1e-9    # mass is conserved
     assert "clocks" in line                                  # null without nvidia-smi
-    assert "cavity_16384_bgk" in line["extra"]               # configs[3] rides along at N = 1
+    # the benchmarked run checks itself against the oracle (device-resident
+    # region and the end-to-end run)
+    par = line["parity"]
+    assert par["ok"] is True and par["max_rel_err"] <= 1e-12
+    assert par["e2e_max_rel_err"] <= 1e-12
+    assert par["steps_compared"] == 3 + 9 * reps + 1
+    # configs[3] rides along, with its own parity
+    assert "cavity" in line["extra"] and "cavity_16384_bgk" in line
+    assert line["extra"]["cavity"]["parity"]["ok"] is True
+    assert line["extra"]["cavity"]["scaling"] == "strong"
 
 
 def test_depth_three_is_accounted_for():
@@ -88,7 +100,9 @@ def test_depth_three_is_accounted_for():
         else:
             os.environ[env_key] = old
     roof = line["roofline"]
-    assert roof["triples"] == 3 and roof["pairs"] == 1 and roof["single_steps"] == 0
+    reps = line["repeats"]
+    assert roof["triples"] == 3 * reps and roof["pairs"] == reps and roof["single_steps"] == 0
+    assert line["parity"]["ok"] is True
     assert roof["steps_per_launch"] == 3 and line["config"]["steps_per_pass"] == 3
     assert line["cpu_baseline"] is None
 

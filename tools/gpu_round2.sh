@@ -15,8 +15,12 @@ el start
 timeout 300 python -m pytest tests/test_gpu_fused.py tests/test_gpu_zz_fused_depth3.py -x -q 2>&1 | tail -5 > $out/${tag}_pytest_fused.log
 el "pytest fused: $(tail -1 $out/${tag}_pytest_fused.log)"
 # 2. two vs three steps per pass, occupancy / ring variants (each line ~7 s)
-timeout 120 python tools/fused_sweep.py $L/libplb.so:PLB_FUSE=0 $L/libplb.so $L/libplb.so:PLB_FUSE_DEPTH=3 > $out/${tag}_sweep.txt 2>&1
-timeout 720 python tools/fused_sweep.py --models mrt \
+timeout 160 python tools/fused_sweep.py $L/libplb.so:PLB_FUSE=0 $L/libplb.so $L/libplb.so:PLB_FUSE_DEPTH=3 > $out/${tag}_sweep.txt 2>&1
+# nine-rate MRT (the literal 9x9 transform), single-step and fused
+timeout 120 python tools/fused_sweep.py --models mrt $L/libplb.so:PLB_MRT_GENERAL=1,PLB_FUSE=0 $L/libplb.so:PLB_MRT_GENERAL=1 \
+    $L/libplb.so:PLB_MRT_GENERAL=1,PLB_FUSE_DEPTH=3 $V/libplb_cb_s1_mb5.so:PLB_MRT_GENERAL=1 $V/libplb_cb_s1_mb4.so:PLB_MRT_GENERAL=1 \
+    $V/libplb_carry_mb4.so:PLB_MRT_GENERAL=1 >> $out/${tag}_sweep.txt 2>&1
+timeout 800 python tools/fused_sweep.py --models mrt \
     $V/libplb_cb_s1_mb5.so $V/libplb_cb_s1_mb6.so $V/libplb_cb_s1_mb4.so $V/libplb_cb_s1_b64_mb10.so \
     $V/libplb_cb_s1_mb5.so:PLB_FUSE_DEPTH=3 $V/libplb_cb_s1_mb5.so:PLB_FUSE_DEPTH=3,PLB_FUSED_ROWS=64 \
     $V/libplb_cb_s1_b64_mb10.so:PLB_FUSE_DEPTH=3 $V/libplb_cb_s1_mb5.so:PLB_FUSED_ROWS=64 \
