@@ -59,9 +59,12 @@ def _stale(target):
 
 def build(force=False, verbose=False, extra_flags=(), variant=None):
     """variant: build lib/variants/libplb_<variant>.so (production flags plus
-    extra_flags) instead of the two shipped libraries -- tuning experiments."""
+    extra_flags) instead of the two shipped libraries -- tuning experiments.
+    Each library is linked under a temporary name and renamed into place, so
+    a tree that is being snapshot never holds a half-written .so; the two
+    shipped libraries are compiled side by side."""
     os.makedirs(LIB_DIR, exist_ok=True)
-    built = []
+    jobs = []
     for strict in (False, True):
         target = lib_path(strict)
         if variant is not None:
@@ -71,17 +74,29 @@ def build(force=False, verbose=False, extra_flags=(), variant=None):
             target = os.path.join(LIB_DIR, "variants", f"libplb_{variant}.so")
         if not force and not _stale(target):
             continue
+        tmp = target + f".tmp{os.getpid()}"
         cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags)
         if strict:
             cmd += ["-fmad=false"]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         cmd += [os.path.join(CSRC, s) for s in SOURCES]
-        cmd += ["-o", target, "-ldl"]
+        cmd += ["-o", tmp, "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
-        subprocess.check_call(cmd, cwd=CSRC)
+        jobs.append((target, tmp, subprocess.Popen(cmd, cwd=CSRC)))
+    built = []
+    failed = None
+    for target, tmp, proc in jobs:
+        if proc.wait() != 0:
+            failed = failed or target
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+            continue
+        os.replace(tmp, target)
         built.append(target)
+    if failed:
+        raise subprocess.CalledProcessError(1, "nvcc (" + failed + ")")
     return built
 
 

@@ -12,6 +12,8 @@ reference; the differences are deliberate and local:
   they live in HBM behind libplb;
 * fp64 only (the north star is an fp64 path).
 """
+import os
+
 import numpy as np
 from types import SimpleNamespace
 
@@ -207,7 +209,8 @@ class Fields:
         self.phase = phase
         self.scalar = scalar
         self.solid = np.zeros(size, dtype=np.bool_)
-        self.solid_id = np.full(size, -1, dtype=int)
+        self.solid_id = np.empty(size, dtype=int)
+        parallel_fill(self.solid_id.reshape(int(domain.shape[0]), -1), -1)
         self.solid_boundary = np.zeros(size, dtype=np.bool_)
         self.fluid_boundary = np.zeros(size, dtype=np.bool_)
         self.surface_normals = np.zeros((size, 2), dtype=prec)
@@ -308,8 +311,85 @@ def _apply_field(spec, field, domain, fields, control, scalar):
                control.precision)
 
 
+def parallel_fill(target, value):
+    """target[...] = value in row blocks on a few threads: filling a fresh
+    multi-GB array is page-fault bound on one core."""
+    n = target.shape[0]
+    row_bytes = max(1, target[:1].nbytes)
+    rows = max(1, (32 << 20) // row_bytes)
+    workers = min(8, os.cpu_count() or 1, -(-n // rows))
+    if workers <= 1:
+        target[...] = value
+        return
+
+    def block(x0):
+        target[x0:x0 + rows] = value
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(workers) as pool:
+        list(pool.map(block, range(0, n, rows)))
+
+
 def _set_field(field, domain, ghost_node, value, func, scalar, precision):
-    control = SimpleNamespace(precision=precision)
+    """Writes `value` / `func(i_global, j_global)` to the non-ghost nodes.
+    The ghost ring is by construction the outermost ring of the padded array
+    (Fields.init_ghost_nodes), so the non-ghost nodes are the inner block of
+    the 2-D view -- no per-node mask, no index arrays of the whole lattice."""
+    nxp, nyp = int(domain.shape[0]), int(domain.shape[1])
+    nx, ny = nxp - 2, nyp - 2
+    ring = ghost_node.reshape(nxp, nyp)
+    if ring[1:-1, 1:-1].any() or not (ring[0].all() and ring[-1].all() and
+                                      ring[:, 0].all() and ring[:, -1].all()):
+        return _set_field_masked(field, domain, ghost_node, value, func, scalar,
+                                 precision)
+    view = field.reshape((nxp, nyp) if scalar else (nxp, nyp, 2))
+    inner = view[1:-1, 1:-1]
+    if func is None:
+        parallel_fill(inner, value)
+        return
+    off_i, off_j = int(domain.offset[0]), int(domain.offset[1])
+    if getattr(func, "vectorized", False):
+        # one call per block of rows, with flat index arrays (i, j) of equal
+        # length; blocks run on a few threads (numpy releases the GIL)
+        rows = max(1, min(nx, (1 << 21) // max(1, ny)))
+        j_row = np.arange(ny, dtype=np.int64) + off_j
+
+        def block(x0):
+            n = min(rows, nx - x0)
+            i_glob = np.repeat(np.arange(x0, x0 + n, dtype=np.int64) + off_i, ny)
+            j_glob = np.tile(j_row, n)
+            result = func(i_glob, j_glob)
+            if scalar:
+                inner[x0:x0 + n] = np.asarray(result, dtype=precision).reshape(n, ny)
+            else:
+                inner[x0:x0 + n, :, 0] = np.asarray(result[0], dtype=precision).reshape(n, ny)
+                inner[x0:x0 + n, :, 1] = np.asarray(result[1], dtype=precision).reshape(n, ny)
+
+        starts = range(0, nx, rows)
+        workers = min(8, os.cpu_count() or 1, len(starts))
+        if workers > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(workers) as pool:
+                list(pool.map(block, starts))
+        else:
+            for x0 in starts:
+                block(x0)
+        return
+    i_glob, j_glob = local_to_global(
+        np.repeat(np.arange(nx, dtype=np.int64), ny),
+        np.tile(np.arange(ny, dtype=np.int64), nx), (off_i, off_j))
+    ufunc = np.frompyfunc(func, 2, 1 if scalar else 2)
+    result = ufunc(i_glob.astype(object), j_glob.astype(object))
+    if scalar:
+        inner[...] = np.asarray(result, dtype=precision).reshape(nx, ny)
+    else:
+        inner[..., 0] = np.asarray(result[0], dtype=precision).reshape(nx, ny)
+        inner[..., 1] = np.asarray(result[1], dtype=precision).reshape(nx, ny)
+
+
+def _set_field_masked(field, domain, ghost_node, value, func, scalar, precision):
+    """The same for a caller-supplied ghost mask that is not the outer ring
+    (read_dict / set_field_* accept any mask, like the reference's)."""
     inner = ~ghost_node
     if func is None:
         field[inner] = value
@@ -318,17 +398,14 @@ def _set_field(field, domain, ghost_node, value, func, scalar, precision):
     i_glob, j_glob = i_glob[inner], j_glob[inner]
     if getattr(func, "vectorized", False):
         result = func(i_glob, j_glob)
-    elif scalar:
-        result = np.frompyfunc(func, 2, 1)(i_glob.astype(object),
-                                           j_glob.astype(object))
     else:
-        result = np.frompyfunc(func, 2, 2)(i_glob.astype(object),
-                                           j_glob.astype(object))
+        result = np.frompyfunc(func, 2, 1 if scalar else 2)(
+            i_glob.astype(object), j_glob.astype(object))
     if scalar:
-        field[inner] = np.asarray(result, dtype=control.precision)
+        field[inner] = np.asarray(result, dtype=precision)
     else:
-        field[inner, 0] = np.asarray(result[0], dtype=control.precision)
-        field[inner, 1] = np.asarray(result[1], dtype=control.precision)
+        field[inner, 0] = np.asarray(result[0], dtype=precision)
+        field[inner, 1] = np.asarray(result[1], dtype=precision)
 
 
 # Sections of initial_fields_dict: (field attribute, scalar?) per key.  The

@@ -42,23 +42,23 @@ timeout 800 python tools/fused_sweep.py --models mrt \
     $L/libplb.so:PLB_FUSE_DEPTH=3,PLB_FUSED_DYNAMIC=1,PLB_FUSED_ROWS=128 >> $out/${tag}_sweep.txt 2>&1
 el sweep
 # 3. the headline line, default and depth 3
-timeout 200 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err
+timeout 500 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 el bench
-PLB_FUSE_DEPTH=3 timeout 100 python bench.py --steps 102 --no-extras --no-cpu-baseline \
+PLB_FUSE_DEPTH=3 timeout 200 python bench.py --steps 102 --no-extras --no-cpu-baseline \
     > $out/${tag}_bench_depth3.json 2> $out/${tag}_bench_depth3.err
 el bench-depth3
 # 4. ncu: the shipped two-step build (its round-1 traffic figure is another build's) and depth 3
 for d in 2 3; do
   PLB_FUSE_DEPTH=$d timeout 150 ncu --set full --clock-control none --import-source on \
       -k regex:k_bulk_fused -s 3 -c 1 -f -o $out/${tag}_ncu_channel_depth$d \
-      python bench.py --steps 6 --warmup 6 --no-extras --no-cpu-baseline > $out/${tag}_ncu_bench_$d.log 2>&1
+      python bench.py --steps 6 --warmup 6 --no-extras --no-cpu-baseline --no-parity > $out/${tag}_ncu_bench_$d.log 2>&1
   ncu -i $out/${tag}_ncu_channel_depth$d.ncu-rep --page raw --csv > $out/${tag}_ncu_raw_channel_depth$d.csv 2>/dev/null
   ncu -i $out/${tag}_ncu_channel_depth$d.ncu-rep --page details > $out/${tag}_ncu_details_channel_depth$d.txt 2>/dev/null
 done
 el ncu
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $out/${tag}_launches_channel.csv \
-    python bench.py --steps 4 --warmup 4 --no-extras --no-cpu-baseline > /dev/null 2>&1
+    python bench.py --steps 4 --warmup 4 --no-extras --no-cpu-baseline --no-parity > /dev/null 2>&1
 el launch-list
 # 5. the rest of the GPU suite
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > $out/${tag}_pytest_all.log
