@@ -609,45 +609,60 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device,
     # after the CPU has touched them (572 ms instead of 59 ms for 3.2 GB)
     plb.download(capi.DENSITY_INNER, rho_out.array)
     plb.download(capi.VELOCITY_INNER, u_out.array)
-    plb.sync()
-    comm.Barrier()
-    t0 = time.perf_counter()
-    plb.event_record(2)
-    plb.upload(capi.DENSITY, rho_in.array)
-    plb.upload(capi.VELOCITY, u_in.array)
-    plb.event_record(4)
-    plb.initialize_pop()
-    for _ in range(steps - 1):
-        solver.execute_single_time_step()
-    solver.single_time_step(store_moments=True)
-    plb.event_record(5)
-    solver.residue_operator.compute_residues(st, solver.backend, comm, steps)
-    plb.event_record(6)
-    plb.download(capi.DENSITY_INNER, rho_out.array)
-    plb.download(capi.VELOCITY_INNER, u_out.array)
-    plb.event_record(3)
-    plb.sync()
-    comm.Barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(plb.event_elapsed_ms(2, 3), 0.0)
-    e2e_ms = allmax(max(e2e_ms, wall_ms))
+    h2d = (rho_in.array.nbytes + u_in.array.nbytes) * world
+    d2h = (rho_out.array.nbytes + u_out.array.nbytes + 48) * world
+
+    def run_e2e(k):
+        plb.sync()
+        comm.Barrier()
+        t0 = time.perf_counter()
+        plb.event_record(2)
+        plb.upload(capi.DENSITY, rho_in.array)
+        plb.upload(capi.VELOCITY, u_in.array)
+        plb.event_record(4)
+        plb.initialize_pop()
+        for _ in range(k - 1):
+            solver.execute_single_time_step()
+        solver.single_time_step(store_moments=True)
+        plb.event_record(5)
+        solver.residue_operator.compute_residues(st, solver.backend, comm, k)
+        plb.event_record(6)
+        plb.download(capi.DENSITY_INNER, rho_out.array)
+        plb.download(capi.VELOCITY_INNER, u_out.array)
+        plb.event_record(3)
+        plb.sync()
+        comm.Barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        total_ms = allmax(max(plb.event_elapsed_ms(2, 3), 0.0, wall_ms))
+        return {"value": total_nodes * k / (total_ms * 1e-3) / 1e9,
+                "unit": "GLUPS", "h2d_bytes_per_step": h2d / k,
+                "d2h_bytes_per_step": d2h / k, "ms_total": total_ms,
+                "steps": k,
+                "breakdown_ms": {
+                    "upload": plb.event_elapsed_ms(2, 4),
+                    "init_and_steps": plb.event_elapsed_ms(4, 5),
+                    "residues": plb.event_elapsed_ms(5, 6),
+                    "download": plb.event_elapsed_ms(6, 3)}}
+
+    # the same run with more steps between the two copies (a production run
+    # saves fields every few hundred steps): the PCIe share shrinks with K
+    long_steps = 10 * steps if steps < 200 else 0
+    e2e_long = run_e2e(long_steps) if long_steps else None
+    e2e = run_e2e(steps)
+    e2e["what"] = ("upload rho,u (pinned) + initialize_pop + K python-issued "
+                   "steps + residues + download rho,u (pinned)")
     mass = np.array([float(rho_out.array.sum())])
     mass_all = np.zeros_like(mass)
     comm.Allreduce(mass, mass_all, op="sum")
-    h2d = (rho_in.array.nbytes + u_in.array.nbytes) * world
-    d2h = (rho_out.array.nbytes + u_out.array.nbytes + 48) * world
-    e2e = {"value": total_nodes * steps / (e2e_ms * 1e-3) / 1e9,
-           "unit": "GLUPS", "h2d_bytes_per_step": h2d / steps,
-           "d2h_bytes_per_step": d2h / steps, "ms_total": e2e_ms,
-           "steps": steps,
-           "what": "upload rho,u (pinned) + initialize_pop + K python-issued "
-                   "steps + residues + download rho,u (pinned)",
-           "breakdown_ms": {
-               "upload": plb.event_elapsed_ms(2, 4),
-               "init_and_steps": plb.event_elapsed_ms(4, 5),
-               "residues": plb.event_elapsed_ms(5, 6),
-               "download": plb.event_elapsed_ms(6, 3)},
-           "global_mean_density": float(mass_all[0]) / total_nodes}
+    e2e["global_mean_density"] = float(mass_all[0]) / total_nodes
+    pcie_ms = e2e["breakdown_ms"]["upload"] + e2e["breakdown_ms"]["download"]
+    e2e["pcie_share"] = pcie_ms / e2e["ms_total"]
+    e2e["pcie_gbs"] = {"h2d": h2d / world / 1e6 / e2e["breakdown_ms"]["upload"],
+                       "d2h": d2h / world / 1e6 / e2e["breakdown_ms"]["download"]}
+    if e2e_long:
+        e2e["same_run_with_10x_steps"] = {k: e2e_long[k] for k in
+                                          ("value", "steps", "ms_total",
+                                           "breakdown_ms")}
     if checker is not None:
         err = allmax(checker.compare(want_e2e, rho_out.array, u_out.array))
         e2e["parity_max_rel_err"] = err
