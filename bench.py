@@ -591,6 +591,8 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device,
                 "peak_source": peak_src,
                 "d2d_copy_gbs_this_box": copy_gbs,
                 "kernel_build": plb.build_info()}
+    mem = plb.memory_info()
+    roofline["device_memory_gb"] = {k: round(v / 1e9, 3) for k, v in mem.items()}
 
     # ---- end to end through the public Solver API, host buffers -----------
     size = plb.size

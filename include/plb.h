@@ -165,6 +165,14 @@ int plb_sync(plb_handle h);
  *        three-step passes executed} */
 int plb_fused_info(plb_handle h, int64_t out[8]);
 
+/* Device memory held by the handle, in bytes (the reference keeps its
+ * `*_device` mirrors for the process lifetime, base/fields.py:192-227):
+ * out = {the two lattices, moment planes (rho, u and the residue's old copy),
+ *        compact scratch lattices of the several-steps-per-pass path incl.
+ *        their index map, node codes / deep flags / lists / staging,
+ *        free device memory, total device memory} */
+int plb_memory_info(plb_handle h, int64_t out[6]);
+
 /* ---- diagnostics ("next" rows) ----------------------------------------- */
 
 /* Residue sums of utils/residues.py:171-222 on the stored moments:

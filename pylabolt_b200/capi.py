@@ -31,7 +31,7 @@ EXPORTS = [
     "plb_host_alloc", "plb_host_free", "plb_flush_l2",
     "plb_profile_enable", "plb_profile_read", "plb_info",
     "plb_link_nodes", "plb_download_link_exchange", "plb_copy_bandwidth",
-    "plb_device_pci_bus_id", "plb_fused_info", "plb_build_info",
+    "plb_device_pci_bus_id", "plb_fused_info", "plb_memory_info", "plb_build_info",
 ]
 STORE_MOMENTS, RECORD_LINKS = 1, 2
 # plb_info()["faces"]: how the slab-face populations travel
@@ -112,6 +112,7 @@ def load_library(strict=None):
                                      ctypes.POINTER(i64)]
     lib.plb_info.argtypes = [vp, ctypes.POINTER(i64)]
     lib.plb_fused_info.argtypes = [vp, ctypes.POINTER(i64)]
+    lib.plb_memory_info.argtypes = [vp, ctypes.POINTER(i64)]
     lib.plb_link_nodes.argtypes = [vp, ctypes.POINTER(i64), i64,
                                    ctypes.POINTER(i64)]
     lib.plb_download_link_exchange.argtypes = [vp, ctypes.POINTER(dbl), i64]
@@ -356,6 +357,14 @@ class Plb:
         keys = ("active", "n_deep", "n_deep3", "n_list1", "pairs", "rows",
                 "strips", "triples")
         return dict(zip(keys, out[:8]))
+
+    def memory_info(self):
+        """Device bytes held by this handle (plb_memory_info)."""
+        out = (ctypes.c_int64 * 6)()
+        self._check(self.lib.plb_memory_info(self._h, out))
+        keys = ("lattices", "moments", "scratch", "flags_lists_staging",
+                "device_free", "device_total")
+        return dict(zip(keys, out[:6]))
 
     def build_info(self):
         """Compile-time kernel configuration of the loaded library."""

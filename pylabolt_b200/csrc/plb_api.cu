@@ -6,6 +6,7 @@
 // exchange over NCCL, loaded at run time with dlopen so that a single-GPU
 // process needs no NCCL at all).
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -168,7 +169,12 @@ struct plb_solver {
     int fuse_mode = PLB_FUSE_DEFAULT;
     int fuse_depth = 2;
     int fused_depth_ok = 0;              // largest depth the geometry qualifies for (0: none)
-    double *f_mid[2] = {nullptr, nullptr};   // scratch lattices (lazy)
+    double *f_mid[2] = {nullptr, nullptr};   // compact scratch lattices (lazy)
+    // node index -> compact scratch lattice, one entry per 16 nodes (lat_off);
+    // entry 0 is a spare segment that absorbs anything unlisted
+    int32_t *mid_map_dev = nullptr;
+    std::vector<int32_t> mid_map_host;
+    int64_t mid_plane = 0;               // doubles per population of a scratch lattice
     uint8_t *deep_dev = nullptr;         // distance to the nearest non-bulk node - 1, capped at 2
     // list p (0-based) = nodes of list pass p + 1 of a depth-d group,
     // lists[d - 2][p]; the last one holds the fluid nodes that are not deep enough
@@ -366,10 +372,11 @@ struct Classifier {
     }
 };
 
-int run_zero_gradient(plb_solver *s, double *fout, cudaStream_t st)
+int run_zero_gradient(plb_solver *s, const StepArgs &a, cudaStream_t st)
 {
     for (auto &z : s->zg_dev)
-        s->launches += launch_zero_gradient(fout, s->L.plane, z.first, z.second, st);
+        s->launches += launch_zero_gradient(a.fout, a.fout_plane, a.fout_map, z.first,
+                                            z.second, st);
     return PLB_OK;
 }
 
@@ -415,6 +422,18 @@ StepArgs step_args(const plb_solver *s, const double *fin, double *fout)
     a.forcing = s->cfg.forcing;
     a.store = 0;
     a.exch = nullptr;
+    a.fin_plane = a.fout_plane = s->L.plane;
+    for (int m = 0; m < 2; ++m) {
+        if (!s->f_mid[m]) continue;
+        if (fin == s->f_mid[m]) {
+            a.fin_map = s->mid_map_dev;
+            a.fin_plane = s->mid_plane;
+        }
+        if (fout == s->f_mid[m]) {
+            a.fout_map = s->mid_map_dev;
+            a.fout_plane = s->mid_plane;
+        }
+    }
     return a;
 }
 
@@ -430,6 +449,12 @@ int edge_chain(plb_solver *s, StepArgs a, unsigned long long t, const LinkNode *
     const Layout &L = s->L;
     cudaStream_t es = s->edge_stream;
     double *fout = a.fout;
+    const int64_t oplane = a.fout_plane;
+    const int32_t *omap = a.fout_map;
+    // offset of population k of node `idx` in fout; a ghost row is contiguous
+    // in a compact lattice too (its segments are allocated in index order)
+    const int32_t *host_map = omap ? s->mid_map_host.data() : nullptr;
+    auto at = [&](int k, int64_t idx) { return k * oplane + lat_off(host_map, idx); };
     const int32_t right_dirs[3] = {1, 5, 8}, left_dirs[3] = {3, 6, 7};
     const bool faces = s->cfg.left_neighbor || s->cfg.right_neighbor;
     // peer-to-peer faces: this step's parity selects the half of the
@@ -461,14 +486,12 @@ int edge_chain(plb_solver *s, StepArgs a, unsigned long long t, const LinkNode *
         // single rank: the periodic image is this rank's own ghost column
         if (s->cfg.left_neighbor)
             s->launches += launch_face_unpack(
-                L, fout, 0, right_dirs, fout, 1 * L.plane + L.at(L.nx, 0),
-                5 * L.plane + L.at(L.nx, 0), 8 * L.plane + L.at(L.nx, 0),
-                s->mask_left, es);
+                L, fout, oplane, omap, 0, right_dirs, fout, at(1, L.at(L.nx, 0)),
+                at(5, L.at(L.nx, 0)), at(8, L.at(L.nx, 0)), s->mask_left, es);
         if (s->cfg.right_neighbor)
             s->launches += launch_face_unpack(
-                L, fout, L.nx - 1, left_dirs, fout, 3 * L.plane + L.at(-1, 0),
-                6 * L.plane + L.at(-1, 0), 7 * L.plane + L.at(-1, 0),
-                s->mask_right, es);
+                L, fout, oplane, omap, L.nx - 1, left_dirs, fout, at(3, L.at(-1, 0)),
+                at(6, L.at(-1, 0)), at(7, L.at(-1, 0)), s->mask_right, es);
     } else if (s->p2p) {
         // the stores are done (stream order): publish step t to the neighbours
         // (mailbox word 0 = "data from your left", word 1 = "from your right")
@@ -481,24 +504,24 @@ int edge_chain(plb_solver *s, StepArgs a, unsigned long long t, const LinkNode *
         const double *mine = reinterpret_cast<const double *>(s->xbuf + XBUF_MAILBOX);
         if (s->left_rank >= 0)
             s->launches += launch_face_unpack(
-                L, fout, 0, right_dirs, mine + par_off, L.y0, L.pitch + L.y0,
+                L, fout, oplane, omap, 0, right_dirs, mine + par_off, L.y0, L.pitch + L.y0,
                 2 * L.pitch + L.y0, s->mask_left, es, mailbox(s->xbuf, 0), t,
                 mailbox(s->xbuf, 2), s->spin_budget);
         if (s->right_rank >= 0)
             s->launches += launch_face_unpack(
-                L, fout, L.nx - 1, left_dirs, mine + 2 * half + par_off, L.y0,
+                L, fout, oplane, omap, L.nx - 1, left_dirs, mine + 2 * half + par_off, L.y0,
                 L.pitch + L.y0, 2 * L.pitch + L.y0, s->mask_right, es,
                 mailbox(s->xbuf, 1), t, mailbox(s->xbuf, 2), s->spin_budget);
     } else {
         NCCL_TRY(g_nccl.GroupStart());
         if (s->right_rank >= 0)
             for (int j = 0; j < 3; ++j)
-                NCCL_TRY(g_nccl.Send(fout + right_dirs[j] * L.plane + L.at(L.nx, 0),
+                NCCL_TRY(g_nccl.Send(fout + at(right_dirs[j], L.at(L.nx, 0)),
                                      size_t(L.ny), ncclDouble, s->right_rank,
                                      s->comm, es));
         if (s->left_rank >= 0)
             for (int j = 0; j < 3; ++j)
-                NCCL_TRY(g_nccl.Send(fout + left_dirs[j] * L.plane + L.at(-1, 0),
+                NCCL_TRY(g_nccl.Send(fout + at(left_dirs[j], L.at(-1, 0)),
                                      size_t(L.ny), ncclDouble, s->left_rank,
                                      s->comm, es));
         if (s->left_rank >= 0)
@@ -511,10 +534,11 @@ int edge_chain(plb_solver *s, StepArgs a, unsigned long long t, const LinkNode *
                                      ncclDouble, s->right_rank, s->comm, es));
         NCCL_TRY(g_nccl.GroupEnd());
         if (s->left_rank >= 0)
-            s->launches += launch_face_unpack(L, fout, 0, right_dirs, s->recv_left,
-                                              0, L.ny, 2 * L.ny, s->mask_left, es);
+            s->launches += launch_face_unpack(L, fout, oplane, omap, 0, right_dirs,
+                                              s->recv_left, 0, L.ny, 2 * L.ny,
+                                              s->mask_left, es);
         if (s->right_rank >= 0)
-            s->launches += launch_face_unpack(L, fout, L.nx - 1, left_dirs,
+            s->launches += launch_face_unpack(L, fout, oplane, omap, L.nx - 1, left_dirs,
                                               s->recv_right, 0, L.ny, 2 * L.ny,
                                               s->mask_right, es);
     }
@@ -546,7 +570,7 @@ int step_once(plb_solver *s, bool store, bool record)
     CUDA_TRY(cudaEventRecord(s->ev_comm, es));
     if (int rc = bulk_timed(s, a, x_lo, x_hi, s->stream, true)) return rc;
     CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
-    run_zero_gradient(s, a.fout, s->stream);
+    run_zero_gradient(s, a, s->stream);
     s->cur ^= 1;
     s->steps_done += 1;
     return PLB_OK;
@@ -575,7 +599,8 @@ int step_fused(plb_solver *s, int depth)
     const Layout &L = s->L;
     for (int m = 0; m < depth - 1; ++m) {
         if (s->f_mid[m]) continue;
-        const size_t bytes = size_t(Q) * L.plane * sizeof(double);
+        // compact: only the 16-node segments the list passes touch (mid_map)
+        const size_t bytes = size_t(Q) * s->mid_plane * sizeof(double);
         if (cudaMalloc(&s->f_mid[m], bytes) != cudaSuccess) {
             cudaGetLastError();
             s->f_mid[m] = nullptr;
@@ -594,11 +619,11 @@ int step_fused(plb_solver *s, int depth)
     for (int p = 0; p < depth; ++p) {
         const double *fin = p == 0 ? A : s->f_mid[p - 1];
         double *fout = p == depth - 1 ? B : s->f_mid[p];
-        if (int rc = edge_chain(s, step_args(s, fin, fout), t1 + p,
-                                s->lists_dev[depth - 2][p], s->n_lists[depth - 2][p],
-                                false, &x_lo, &x_hi))
+        const StepArgs pa = step_args(s, fin, fout);
+        if (int rc = edge_chain(s, pa, t1 + p, s->lists_dev[depth - 2][p],
+                                s->n_lists[depth - 2][p], false, &x_lo, &x_hi))
             return rc;
-        if (p < depth - 1) run_zero_gradient(s, fout, es);
+        if (p < depth - 1) run_zero_gradient(s, pa, es);
     }
     CUDA_TRY(cudaEventRecord(s->ev_comm, es));
 
@@ -628,7 +653,7 @@ int step_fused(plb_solver *s, int depth)
         s->prof_used += 2;
     }
     CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
-    run_zero_gradient(s, B, s->stream);
+    run_zero_gradient(s, a, s->stream);
     s->cur ^= 1;
     s->steps_done += depth;
     s->groups_done[depth - 2] += 1;
@@ -920,6 +945,7 @@ void plb_destroy(plb_handle s)
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (int i = 0; i < 2; ++i) cudaFree(s->f[i]);
     for (int m = 0; m < 2; ++m) cudaFree(s->f_mid[m]);
+    cudaFree(s->mid_map_dev);
     cudaFree(s->deep_dev);
     cudaFree(s->work_counter);
     for (int d = 0; d < 2; ++d)
@@ -1000,6 +1026,16 @@ int plb_finalize_geometry(plb_handle s)
     CUDA_TRY(cudaSetDevice(s->cfg.device));
     const Layout &L = s->L;
     const int64_t nx = L.nx, ny = L.ny, nyp = ny + 2;
+    // PLB_SETUP_TIMING=1: wall clock of the phases below on stderr
+    const bool timing = getenv("PLB_SETUP_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[plb setup] %-28s %8.1f ms\n", what,
+                std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
 
     // links owned by boundary elements; later elements win, zero_gradient
     // elements are a final pass (see oracle_set_boundary)
@@ -1015,6 +1051,7 @@ int plb_finalize_geometry(plb_handle s)
             }
     }
     Classifier cls{s, nx, ny, nyp, s->solid_host.data(), &element_of, &zg_cover};
+    lap("element maps");
 
     // rows (reference x) that contain any solid node, ghost ring included
     std::vector<uint8_t> row_has_solid(size_t(nx + 2), 0);
@@ -1029,36 +1066,48 @@ int plb_finalize_geometry(plb_handle s)
     std::vector<uint8_t> code(size_t(L.plane), NODE_GHOST);
     std::vector<LinkNode> link_nodes;
     int64_t n_bulk = 0, n_solid = 0;
+    // row_class[r] (padded row r = x + 1): rows whose interior columns
+    // 1 .. ny - 2 are all BULK get the class (bulk-ness of y = 0, of y = ny - 1)
+    // in 0 .. 3, every other row -1 -- rows of one class have identical
+    // BULK / non-BULK patterns, which is all the deep flags depend on
+    std::vector<int8_t> row_class(size_t(nx + 2), -1);
+    auto classify = [&](int64_t x, int64_t y, uint8_t *crow) {
+        if (cls.is_solid(x, y)) {
+            crow[y] = NODE_SOLID;
+            ++n_solid;
+            return;
+        }
+        const uint64_t lk = cls.links(x, y);
+        if (lk == 0) {
+            crow[y] = NODE_BULK;
+            ++n_bulk;
+            if (x == 0) ++s->n_bulk_edge[0];
+            if (x == nx - 1 && nx > 1) ++s->n_bulk_edge[1];
+        } else {
+            crow[y] = NODE_LINK;
+            link_nodes.push_back(LinkNode{int32_t(x), int32_t(y), lk});
+        }
+    };
     for (int64_t x = 0; x < nx; ++x) {
         uint8_t *crow = code.data() + L.at(x, 0);
         const bool near_solid =
             row_has_solid[x] || row_has_solid[x + 1] || row_has_solid[x + 2];
         const bool edge_row = x == 0 || x == nx - 1;
-        for (int64_t y = 0; y < ny; ++y) {
-            if (!near_solid && !edge_row && y > 0 && y < ny - 1) {
-                crow[y] = NODE_BULK;
-                ++n_bulk;
-                continue;
-            }
-            if (cls.is_solid(x, y)) {
-                crow[y] = NODE_SOLID;
-                ++n_solid;
-                continue;
-            }
-            const uint64_t lk = cls.links(x, y);
-            if (lk == 0) {
-                crow[y] = NODE_BULK;
-                ++n_bulk;
-                if (x == 0) ++s->n_bulk_edge[0];
-                if (x == nx - 1 && nx > 1) ++s->n_bulk_edge[1];
-            } else {
-                crow[y] = NODE_LINK;
-                link_nodes.push_back(LinkNode{int32_t(x), int32_t(y), lk});
-            }
+        if (!near_solid && !edge_row && ny >= 2) {
+            // every interior column pushes to plain fluid neighbours
+            classify(x, 0, crow);
+            memset(crow + 1, NODE_BULK, size_t(ny - 2));
+            n_bulk += ny - 2;
+            classify(x, ny - 1, crow);
+            row_class[size_t(x + 1)] = int8_t((crow[0] == NODE_BULK ? 1 : 0) |
+                                              (crow[ny - 1] == NODE_BULK ? 2 : 0));
+            continue;
         }
+        for (int64_t y = 0; y < ny; ++y) classify(x, y, crow);
     }
     s->n_bulk = n_bulk;
     s->n_solid = n_solid;
+    lap("node codes");
 
     // slab-face acceptance masks: slot (node, k) is fed from across the face
     // iff the node is fluid and its own link in direction inv(k) is a push
@@ -1093,19 +1142,71 @@ int plb_finalize_geometry(plb_handle s)
         const int64_t P = L.pitch, N = L.plane;
         std::vector<uint8_t> deep(size_t(N), 0);
         {
-            std::vector<uint8_t> h(size_t(N), 1), bad(size_t(N), 1);
+            // bad1 = a non-bulk code (BULK = 0) in the 3 x 3 neighbourhood,
+            // bad2 = a bad1 in the 3 x 3 neighbourhood, deep = !bad1 + !bad2:
+            // two separable 3 x 3 dilations, streamed row by row through
+            // cache-sized row buffers (no whole-plane temporaries).  Five
+            // consecutive rows of one row_class have one and the same deep
+            // row, which is then copied instead of recomputed -- all but
+            // O(1) rows of a lattice without obstacles.
+            const int64_t R = nx + 2;
             const uint8_t *c = code.data();
-            // level 1: no non-bulk code (BULK = 0) in the 3 x 3 neighbourhood
-            for (int64_t i = 1; i + 1 < N; ++i) h[size_t(i)] = c[i - 1] | c[i] | c[i + 1];
-            for (int64_t i = P; i + P < N; ++i)
-                bad[size_t(i)] = (h[size_t(i - P)] | h[size_t(i)] | h[size_t(i + P)]) != 0;
-            // level 2: no level-1 failure in the 3 x 3 neighbourhood
-            for (int64_t i = 1; i + 1 < N; ++i)
-                h[size_t(i)] = bad[size_t(i - 1)] | bad[size_t(i)] | bad[size_t(i + 1)];
-            for (int64_t i = P; i + P < N; ++i)
-                deep[size_t(i)] = uint8_t(!bad[size_t(i)]) +
-                                  uint8_t((h[size_t(i - P)] | h[size_t(i)] | h[size_t(i + P)]) == 0);
+            auto hor = [P](const uint8_t *in, uint8_t *out) {
+                // out[i] = in[i-1] | in[i] | in[i+1]; the row ends are
+                // alignment padding (GHOST, non-bulk) and stay "bad"
+                out[0] = out[P - 1] = 1;
+                for (int64_t i = 1; i + 1 < P; ++i) out[i] = in[i - 1] | in[i] | in[i + 1];
+            };
+            // ring buffers over padded rows: h1[r] (codes dilated along y),
+            // b1[r] (bad1), h2[r] (bad1 dilated along y)
+            std::vector<uint8_t> h1buf(size_t(3 * P)), b1buf(size_t(3 * P)), h2buf(size_t(3 * P));
+            auto h1 = [&](int64_t r) { return h1buf.data() + (r % 3) * P; };
+            auto b1 = [&](int64_t r) { return b1buf.data() + (r % 3) * P; };
+            auto h2 = [&](int64_t r) { return h2buf.data() + (r % 3) * P; };
+            // b1[r] needs h1[r-1 .. r+1], deep[r] needs b1[r] and h2[r-1 .. r+1];
+            // the ghost rows 0 and R - 1 are bad by definition
+            auto make_h1 = [&](int64_t r) { hor(c + r * P, h1(r)); };
+            std::vector<uint8_t> tmpl[4];
+            int64_t h1_next = 0;       // next padded row whose h1 is to be made
+            int64_t b1_next = 0;       // next row whose b1 / h2 is to be made
+            auto advance_b1 = [&](int64_t upto) {
+                // make b1 / h2 for rows b1_next .. upto (inclusive)
+                for (; b1_next <= upto; ++b1_next) {
+                    const int64_t r = b1_next;
+                    for (; h1_next <= r + 1 && h1_next < R; ++h1_next) make_h1(h1_next);
+                    uint8_t *o = b1(r);
+                    if (r == 0 || r == R - 1) {
+                        memset(o, 1, size_t(P));
+                    } else {
+                        const uint8_t *u = h1(r - 1), *m = h1(r), *d = h1(r + 1);
+                        for (int64_t i = 0; i < P; ++i) o[i] = (u[i] | m[i] | d[i]) != 0;
+                    }
+                    hor(o, h2(r));
+                }
+            };
+            for (int64_t r = 1; r + 1 < R; ++r) {
+                uint8_t *out = deep.data() + r * P;
+                const int8_t k = row_class[size_t(r)];
+                const bool uniform = k >= 0 && r >= 3 && r + 3 < R &&
+                    row_class[size_t(r - 2)] == k && row_class[size_t(r - 1)] == k &&
+                    row_class[size_t(r + 1)] == k && row_class[size_t(r + 2)] == k;
+                if (uniform && !tmpl[k].empty()) {
+                    memcpy(out, tmpl[k].data(), size_t(P));
+                    continue;
+                }
+                // the streaming state may lag behind after copied rows
+                if (b1_next < r - 1) {
+                    b1_next = r - 1;
+                    h1_next = r - 2;
+                }
+                advance_b1(r + 1);
+                const uint8_t *u = h2(r - 1), *m = h2(r), *d = h2(r + 1), *bad = b1(r);
+                for (int64_t i = 0; i < P; ++i)
+                    out[i] = uint8_t(!bad[i]) + uint8_t((u[i] | m[i] | d[i]) == 0);
+                if (uniform) tmpl[k].assign(out, out + P);
+            }
         }
+        lap("deep flags");
         // candidates: interior nodes that are not fully deep (a few rings)
         std::vector<int64_t> candidates;
         for (int64_t x = 0; x < nx; ++x) {
@@ -1121,8 +1222,12 @@ int plb_finalize_geometry(plb_handle s)
                 ++y;
             }
         }
+        lap("candidates");
         const int64_t n_fluid = n_bulk + int64_t(link_nodes.size());
         std::vector<uint8_t> on(size_t(N), 0);
+        // 16-node segments of the plane that a list pass reads or writes in a
+        // scratch lattice: the listed nodes and their eight neighbours
+        std::vector<uint8_t> seg_used(size_t(N / 16), 0);
         const int64_t nb8[8] = {-1, 1, -P, -P - 1, -P + 1, P, P - 1, P + 1};
         for (int depth = 2; depth <= s->fuse_depth; ++depth) {
             const uint8_t need = uint8_t(depth - 1);
@@ -1164,6 +1269,11 @@ int plb_finalize_geometry(plb_handle s)
                              (int64_t(lists[0].size()) * 8 <= n_fluid && n_fluid >= 4096));
             if (!ok) continue;
             s->fused_depth_ok = depth;
+            for (int64_t idx : lists[0])
+                for (int64_t dx = -P; dx <= P; dx += P) {
+                    seg_used[size_t((idx + dx - 1) >> 4)] = 1;
+                    seg_used[size_t((idx + dx + 1) >> 4)] = 1;
+                }
             for (int p = 0; p < depth; ++p) {
                 // index -> record; link nodes (all on every list) keep their codes
                 std::vector<LinkNode> l;
@@ -1190,7 +1300,24 @@ int plb_finalize_geometry(plb_handle s)
                                     l.size() * sizeof(LinkNode), cudaMemcpyHostToDevice));
             }
         }
+        lap("lists");
         if (s->fused_depth_ok >= 2) {
+            // compact scratch lattices: the two ghost rows (send staging of the
+            // slab faces, contiguous) and every used segment, numbered in index
+            // order from 1; segment 0 is a spare that absorbs the rest
+            const int64_t segs_per_row = P / 16;
+            for (int64_t i = 0; i < segs_per_row; ++i)
+                seg_used[size_t(i)] = seg_used[size_t((nx + 1) * segs_per_row + i)] = 1;
+            s->mid_map_host.assign(seg_used.size(), 0);
+            int32_t n_seg = 1;
+            for (size_t i = 0; i < seg_used.size(); ++i)
+                if (seg_used[i]) s->mid_map_host[i] = n_seg++;
+            s->mid_plane = int64_t(n_seg) * 16;
+            CUDA_TRY(cudaMalloc(&s->mid_map_dev, s->mid_map_host.size() * sizeof(int32_t)));
+            CUDA_TRY(cudaMemcpy(s->mid_map_dev, s->mid_map_host.data(),
+                                s->mid_map_host.size() * sizeof(int32_t),
+                                cudaMemcpyHostToDevice));
+            lap("scratch map");
             if (const char *v = getenv("PLB_FUSED_DYNAMIC"))
                 if (atoi(v) != 0) CUDA_TRY(cudaMalloc(&s->work_counter, 256));
             CUDA_TRY(cudaMalloc(&s->deep_dev, deep.size()));
@@ -1208,6 +1335,7 @@ int plb_finalize_geometry(plb_handle s)
         }
     }
 
+    lap("deep upload");
     // device copies
     CUDA_TRY(cudaMemcpy(s->code, code.data(), code.size(), cudaMemcpyHostToDevice));
     s->n_links = int64_t(link_nodes.size());
@@ -1253,6 +1381,7 @@ int plb_finalize_geometry(plb_handle s)
     CUDA_TRY(cudaMalloc(&s->mask_right, size_t(ny)));
     CUDA_TRY(cudaMemcpy(s->mask_left, mask_l.data(), size_t(ny), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(s->mask_right, mask_r.data(), size_t(ny), cudaMemcpyHostToDevice));
+    lap("device copies");
     s->finalized = true;
     return PLB_OK;
 }
@@ -1365,6 +1494,29 @@ int plb_fused_info(plb_handle s, int64_t out[8])
     out[5] = s->fused_rows;
     out[6] = fused_strips(s->L, d >= 2 ? d : 2);
     out[7] = s->groups_done[1];
+    return PLB_OK;
+}
+
+int plb_memory_info(plb_handle s, int64_t out[6])
+{
+    if (!s || !out) return fail(PLB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    const int64_t plane_bytes = s->L.plane * int64_t(sizeof(double));
+    out[0] = 2 * Q * plane_bytes;
+    out[1] = (s->mom ? 3 : 0) * plane_bytes + (s->mom_old ? 3 : 0) * plane_bytes;
+    out[2] = 0;
+    for (int m = 0; m < 2; ++m)
+        if (s->f_mid[m]) out[2] += Q * s->mid_plane * int64_t(sizeof(double));
+    if (s->mid_map_dev) out[2] += int64_t(s->mid_map_host.size() * sizeof(int32_t));
+    int64_t lists = s->n_links * int64_t(sizeof(LinkNode));
+    for (int d = 0; d < 2; ++d)
+        for (int p = 0; p < 3; ++p) lists += s->n_lists[d][p] * int64_t(sizeof(LinkNode));
+    out[3] = s->L.plane * (s->deep_dev ? 2 : 1) + lists + 2 * int64_t(s->staging_bytes) +
+             (s->exch_dev ? s->n_links * 8 * int64_t(sizeof(double)) : 0);
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    out[4] = int64_t(free_b);
+    out[5] = int64_t(total_b);
     return PLB_OK;
 }
 

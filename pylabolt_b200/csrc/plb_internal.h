@@ -105,7 +105,22 @@ struct StepArgs {
     // the edge-column and link kernels.  Null: this rank's own ghost rows.
     double *face_lo = nullptr, *face_hi = nullptr;
     int64_t face_stride = 0;
+    // Compact lattices (the scratch lattices of the several-steps-per-pass
+    // path hold time t + 1 (t + 2) on the O(perimeter) listed nodes only):
+    // `*_map` translates a node index into the compact lattice, 16 nodes (one
+    // 128-byte line) at a time, `*_plane` is the stride between populations.
+    // Null map: an ordinary full lattice (plane = L.plane).  Only the
+    // list-driven kernels (k_links, k_zero_gradient, k_face_unpack) and
+    // push_dst translate; the bulk kernels always work on full lattices.
+    const int32_t *fin_map = nullptr, *fout_map = nullptr;
+    int64_t fin_plane = 0, fout_plane = 0;
 };
+
+// node index -> offset inside one population plane of a (possibly compact) lattice
+__host__ __device__ inline int64_t lat_off(const int32_t *map, int64_t idx)
+{
+    return map ? ((int64_t(map[idx >> 4]) << 4) | (idx & 15)) : idx;
+}
 
 // ---- launchers implemented in plb_kernels.cu ---------------------------
 // All return the number of kernels launched (0 if nothing to do).
@@ -132,11 +147,13 @@ int launch_links(const StepArgs &a, const LinkNode *nodes, int64_t n_nodes,
 // (either pointer may be null).
 int launch_face_signal(unsigned long long *flag_a, unsigned long long *flag_b,
                        unsigned long long value, cudaStream_t stream);
-int launch_zero_gradient(double *fout, int64_t plane, const ZgLink *links,
-                         int64_t n_links, cudaStream_t stream);
+int launch_zero_gradient(double *fout, int64_t plane, const int32_t *map,
+                         const ZgLink *links, int64_t n_links, cudaStream_t stream);
 // Copies the three face populations from `src` (three rows of ny doubles,
-// src_stride apart) into column x_col of fout where mask bit j is set.
-int launch_face_unpack(const Layout &L, double *fout, int64_t x_col,
+// src_stride apart) into column x_col of fout where mask bit j is set
+// (fout: stride `plane` between populations, node index through `map`).
+int launch_face_unpack(const Layout &L, double *fout, int64_t plane,
+                       const int32_t *map, int64_t x_col,
                        const int32_t dirs[3], const double *src,
                        int64_t src_stride0, int64_t src_stride1,
                        int64_t src_stride2, const uint8_t *mask,

@@ -168,7 +168,7 @@ __device__ __forceinline__ double *push_dst(const StepArgs &a, int q, int64_t tx
         return a.face_lo + slot * a.face_stride + L.y0 + ty;
     if (tx >= L.nx && a.face_hi)
         return a.face_hi + slot * a.face_stride + L.y0 + ty;
-    return a.fout + q * L.plane + L.at(tx, ty);
+    return a.fout + q * a.fout_plane + lat_off(a.fout_map, L.at(tx, ty));
 }
 
 template <int COLL, int FORCING, bool STORE>
@@ -817,7 +817,9 @@ __device__ __forceinline__ void node_velocity(const StepArgs &a, int64_t idx,
     if (c == NODE_BULK || c == NODE_LINK) {
         double f[Q];
 #pragma unroll
-        for (int k = 0; k < Q; ++k) f[k] = a.fin[k * a.p.L.plane + idx];
+        const int64_t off = lat_off(a.fin_map, idx);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) f[k] = a.fin[k * a.fin_plane + off];
         const Moments m = moments(a.p, f);
         ux = m.ux;
         uy = m.uy;
@@ -836,19 +838,22 @@ k_links(StepArgs a, const LinkNode *__restrict__ nodes, int64_t n_nodes,
     if (i >= n_nodes) return;
     const LinkNode nd = nodes[i];
     const Layout &L = a.p.L;
-    const int64_t plane = L.plane, pitch = L.pitch;
+    const int64_t pitch = L.pitch;
     const int64_t idx = L.at(nd.x, nd.y);
+    // the node's own place in the input / output lattice (full or compact)
+    const int64_t in_off = lat_off(a.fin_map, idx);
+    const int64_t out_off = lat_off(a.fout_map, idx);
 
     double f[Q], g[Q];
 #pragma unroll
-    for (int k = 0; k < Q; ++k) f[k] = a.fin[k * plane + idx];
+    for (int k = 0; k < Q; ++k) f[k] = a.fin[k * a.fin_plane + in_off];
     const Moments m = collide<COLL, FORCING>(a.p, f, g);
     if constexpr (STORE) {
         a.rho[idx] = m.rho;
         a.ux[idx] = m.ux;
         a.uy[idx] = m.uy;
     }
-    a.fout[idx] = g[0];   // pop_new[ind, 0] = pop[ind, 0], streaming_kernels.py:34
+    a.fout[out_off] = g[0];   // pop_new[ind, 0] = pop[ind, 0], streaming_kernels.py:34
 
 #pragma unroll
     for (int q = 1; q < Q; ++q) {
@@ -901,7 +906,7 @@ k_links(StepArgs a, const LinkNode *__restrict__ nodes, int64_t n_nodes,
         } else {
             own = false;      // LINK_ZG: written by k_zero_gradient afterwards
         }
-        if (own) a.fout[qi * plane + idx] = back;
+        if (own) a.fout[qi * a.fout_plane + out_off] = back;
         // momentum exchanged across the link, for the wall / obstacle force:
         // pop[k] c_k - pop_new[k_inv] c_kinv = c_k (g_k + f'_kinv)
         // (cpu/force_torque_kernels.py:73-81, 128-137)
@@ -911,12 +916,13 @@ k_links(StepArgs a, const LinkNode *__restrict__ nodes, int64_t n_nodes,
 
 // zero_gradient (our definition, see oracle/plb_oracle.c bc_zero_gradient)
 __global__ void k_zero_gradient(double *fout, int64_t plane,
+                                const int32_t *__restrict__ map,
                                 const ZgLink *__restrict__ links, int64_t n)
 {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const ZgLink l = links[i];
-    fout[l.v * plane + l.dst] = fout[l.v * plane + l.src];
+    fout[l.v * plane + lat_off(map, l.dst)] = fout[l.v * plane + lat_off(map, l.src)];
 }
 
 // Peer-to-peer hand-shake.  The edge-column and link kernels of step t have
@@ -950,8 +956,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(
 // faces every CTA first waits until the neighbour has published step
 // `wait_value` in this rank's mailbox; a neighbour that never arrives sets
 // *status after `spin_budget` clock cycles instead of hanging the GPU.
-__global__ void k_face_unpack(Layout L, double *fout, int64_t x_col, int32_t k0,
-                              int32_t k1, int32_t k2,
+__global__ void k_face_unpack(Layout L, double *fout, int64_t plane,
+                              const int32_t *__restrict__ map, int64_t x_col,
+                              int32_t k0, int32_t k1, int32_t k2,
                               const double *__restrict__ src, int64_t s0,
                               int64_t s1, int64_t s2,
                               const uint8_t *__restrict__ mask,
@@ -977,10 +984,11 @@ __global__ void k_face_unpack(Layout L, double *fout, int64_t x_col, int32_t k0,
     const int64_t y = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (y >= L.ny) return;
     const uint8_t mk = mask[y];
-    const int64_t idx = L.at(x_col, y);
-    if (mk & 1) fout[k0 * L.plane + idx] = __ldcg(src + s0 + y);
-    if (mk & 2) fout[k1 * L.plane + idx] = __ldcg(src + s1 + y);
-    if (mk & 4) fout[k2 * L.plane + idx] = __ldcg(src + s2 + y);
+    if (!mk) return;
+    const int64_t idx = lat_off(map, L.at(x_col, y));
+    if (mk & 1) fout[k0 * plane + idx] = __ldcg(src + s0 + y);
+    if (mk & 2) fout[k1 * plane + idx] = __ldcg(src + s1 + y);
+    if (mk & 4) fout[k2 * plane + idx] = __ldcg(src + s2 + y);
 }
 
 // ---------------------------------------------------------------------------
@@ -1322,16 +1330,17 @@ int launch_links(const StepArgs &a, const LinkNode *nodes, int64_t n_nodes,
     return 1;
 }
 
-int launch_zero_gradient(double *fout, int64_t plane, const ZgLink *links,
-                         int64_t n_links, cudaStream_t stream)
+int launch_zero_gradient(double *fout, int64_t plane, const int32_t *map,
+                         const ZgLink *links, int64_t n_links, cudaStream_t stream)
 {
     if (n_links <= 0) return 0;
     PLB_LAUNCH(SIMPLE, (k_zero_gradient), unsigned((n_links + 127) / 128), 128, stream, fout,
-               plane, links, n_links);
+               plane, map, links, n_links);
     return 1;
 }
 
-int launch_face_unpack(const Layout &L, double *fout, int64_t x_col,
+int launch_face_unpack(const Layout &L, double *fout, int64_t plane,
+                       const int32_t *map, int64_t x_col,
                        const int32_t dirs[3], const double *src,
                        int64_t src_stride0, int64_t src_stride1,
                        int64_t src_stride2, const uint8_t *mask,
@@ -1340,7 +1349,7 @@ int launch_face_unpack(const Layout &L, double *fout, int64_t x_col,
                        long long spin_budget)
 {
     PLB_LAUNCH(COOP, (k_face_unpack), unsigned((L.ny + 255) / 256), 256, stream, L, fout,
-               x_col, dirs[0], dirs[1], dirs[2], src, src_stride0, src_stride1, src_stride2,
+               plane, map, x_col, dirs[0], dirs[1], dirs[2], src, src_stride0, src_stride1, src_stride2,
                mask, wait_flag, wait_value, status, spin_budget);
     return 1;
 }

@@ -422,6 +422,11 @@ const char *cudaGetErrorString(cudaError_t e)
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 cudaError_t cudaGetDeviceCount(int *n) { *n = 8; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaMemGetInfo(size_t *free_b, size_t *total_b)
+{
+    *free_b = *total_b = size_t(180) << 30;
+    return cudaSuccess;
+}
 cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 1000000; return cudaSuccess; }
 cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -1; return cudaSuccess; }
 cudaError_t cudaDeviceGetPCIBusId(char *buf, int len, int)

@@ -52,6 +52,7 @@ extern "C" {
 const char *cudaGetErrorString(cudaError_t);
 cudaError_t cudaGetLastError(void);
 cudaError_t cudaGetDeviceCount(int *);
+cudaError_t cudaMemGetInfo(size_t *free_b, size_t *total_b);
 cudaError_t cudaSetDevice(int);
 cudaError_t cudaDeviceGetAttribute(int *, cudaDeviceAttr, int);
 cudaError_t cudaDeviceGetStreamPriorityRange(int *, int *);
