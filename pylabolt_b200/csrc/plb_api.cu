@@ -880,6 +880,49 @@ int plb_create(const plb_config *c, plb_handle *out)
             t.k2cg[j] = t.k2 * cg[j];
         }
     }
+    {
+        // lattice sums for the nine-rate MRT in moment space (MrtMoments)
+        static const int M[Q][Q] = {
+            {1, 1, 1, 1, 1, 1, 1, 1, 1},      {-4, -1, -1, -1, -1, 2, 2, 2, 2},
+            {4, -2, -2, -2, -2, 1, 1, 1, 1},  {0, 1, 0, -1, 0, 1, -1, -1, 1},
+            {0, -2, 0, 2, 0, 1, -1, -1, 1},   {0, 0, 1, 0, -1, 1, 1, -1, -1},
+            {0, 0, -2, 0, 2, 1, 1, -1, -1},   {0, 1, -1, 1, -1, 0, 0, 0, 0},
+            {0, 0, 0, 0, 0, 1, -1, 1, -1}};
+        double A[Q], Bx[Q], By[Q], Cxx[Q], Cyy[Q], Cxy[Q], norm2[Q];
+        for (int r = 0; r < Q; ++r) {
+            A[r] = Bx[r] = By[r] = Cxx[r] = Cyy[r] = Cxy[r] = norm2[r] = 0.0;
+            for (int k = 0; k < Q; ++k) {
+                const double mw = M[r][k] * p.w[k];
+                A[r] += mw;
+                Bx[r] += mw * CX[k];
+                By[r] += mw * CY[k];
+                Cxx[r] += mw * CX[k] * CX[k];
+                Cyy[r] += mw * CY[k] * CY[k];
+                Cxy[r] += mw * CX[k] * CY[k];
+                norm2[r] += double(M[r][k] * M[r][k]);
+            }
+        }
+        MrtMoments &t = p.mrtm;
+        for (int r = 0; r < 3; ++r) {
+            t.A[r] = A[r];
+            t.Qx[r] = 0.5 * p.inv_cs_4 * Cxx[r] - 0.5 * p.inv_cs_2 * A[r];
+            t.Qy[r] = 0.5 * p.inv_cs_4 * Cyy[r] - 0.5 * p.inv_cs_2 * A[r];
+            t.GA[r] = p.inv_cs_2 * A[r];
+            t.Gx[r] = p.inv_cs_4 * Cxx[r];
+            t.Gy[r] = p.inv_cs_4 * Cyy[r];
+        }
+        t.B[0] = p.inv_cs_2 * Bx[3];
+        t.B[1] = p.inv_cs_2 * Bx[4];
+        t.B[2] = p.inv_cs_2 * By[5];
+        t.B[3] = p.inv_cs_2 * By[6];
+        t.Q7x = 0.5 * p.inv_cs_4 * Cxx[7];
+        t.Q7y = 0.5 * p.inv_cs_4 * Cyy[7];
+        t.Q8 = p.inv_cs_4 * Cxy[8];
+        for (int r = 0; r < Q; ++r) {
+            t.sn[r] = p.s[r] / norm2[r];
+            t.hn[r] = (1.0 - 0.5 * p.s[r]) / norm2[r];
+        }
+    }
     if (const char *v = getenv("PLB_KERNEL"))
         s->variant = (strcmp(v, "scalar") == 0) ? 0 : 1;
     if (const char *v = getenv("PLB_FUSE")) s->fuse_mode = atoi(v);

@@ -186,35 +186,68 @@ __device__ __forceinline__ void mrt_backward(const double c[Q], double v[Q])
     v[8] = dg + qx - qy - c[8];
 }
 
-// MRT -- OUR DEFINITION (no upstream kernel):
+// MRT with nine free rates -- OUR DEFINITION (no upstream kernel; SURVEY.md
+// App. A.2):
 //   g = f - Minv diag(S) M (f - feq) + Minv (I - diag(S)/2) M Phi
+// evaluated in MOMENT space: m = M f is formed once (it also yields rho and
+// the momentum), the moments of feq and of the Guo source Phi are low-order
+// polynomials in (rho, u, F) with host-computed coefficients (MrtMoments), and
+//   g = f + Minv [ S (m_eq - m) + (I - S/2) m_Phi ].
+// ~165 fp64 operations per node with second-order Guo forcing; the
+// population-space form (nine feq, nine Phi, two forward transforms) needed
+// 304 and was fp64-bound.  The 9 x 9 transforms stay unrolled in registers.
 template <int FORCING>
-__device__ __forceinline__ void mrt_all(const KParams &p, const Moments &m,
-                                        double u2, const double f[Q],
-                                        double g[Q])
+__device__ __forceinline__ Moments collide_mrt_moments(const KParams &p,
+                                                       const double f[Q],
+                                                       double g[Q])
 {
-    constexpr double inv_norm2[Q] = {1.0 / 9,  1.0 / 36, 1.0 / 36,
-                                     1.0 / 6,  1.0 / 12, 1.0 / 6,
-                                     1.0 / 12, 1.0 / 4,  1.0 / 4};
-    double e[Q], fneq[Q], mom[Q], c[Q];
-    feq_all(p, m, u2, e);
+    const MrtMoments &t = p.mrtm;
+    double mom[Q], c[Q];
+    mrt_forward(f, mom);
+    Moments m;
+    m.rho = mom[0];
+    m.fx = m.rho * p.gx;
+    m.fy = m.rho * p.gy;
+    const double inv = 1.0 / (m.rho + p.eps);
+    // u = (sum_k c_k f_k + F/2) / rho, cpu/compute_fields_kernels.py:55-65
+    m.ux = (mom[3] + 0.5 * m.fx) * inv;
+    m.uy = (mom[5] + 0.5 * m.fy) * inv;
+    const double ux = m.ux, uy = m.uy, rho = m.rho;
+    const double uxx = ux * ux, uyy = uy * uy;
+    const double jx = rho * ux, jy = rho * uy;
 #pragma unroll
-    for (int k = 0; k < Q; ++k) fneq[k] = f[k] - e[k];
-    mrt_forward(fneq, mom);
+    for (int r = 0; r < 3; ++r)
+        c[r] = t.sn[r] * (rho * (t.A[r] + t.Qx[r] * uxx + t.Qy[r] * uyy) - mom[r]);
+    c[3] = t.sn[3] * (t.B[0] * jx - mom[3]);
+    c[4] = t.sn[4] * (t.B[1] * jx - mom[4]);
+    c[5] = t.sn[5] * (t.B[2] * jy - mom[5]);
+    c[6] = t.sn[6] * (t.B[3] * jy - mom[6]);
+    c[7] = t.sn[7] * (rho * (t.Q7x * uxx + t.Q7y * uyy) - mom[7]);
+    c[8] = t.sn[8] * (t.Q8 * (jx * uy) - mom[8]);
+    if constexpr (FORCING == 1) {
+        // linear Guo source w_k (c_k . F) / cs^2: momentum-like moments only
+        c[3] += t.hn[3] * (t.B[0] * m.fx);
+        c[4] += t.hn[4] * (t.B[1] * m.fx);
+        c[5] += t.hn[5] * (t.B[2] * m.fy);
+        c[6] += t.hn[6] * (t.B[3] * m.fy);
+    } else if constexpr (FORCING == 2) {
+        const double xfx = ux * m.fx, yfy = uy * m.fy;
+        const double uf = xfx + yfy;
 #pragma unroll
-    for (int r = 0; r < Q; ++r) c[r] = -(p.s[r] * inv_norm2[r]) * mom[r];
-    if constexpr (FORCING != 0) {
-        double phi[Q], mphi[Q];
-        guo_all<FORCING>(p, m, phi);
-        mrt_forward(phi, mphi);
-#pragma unroll
-        for (int r = 0; r < Q; ++r)
-            c[r] += ((1.0 - 0.5 * p.s[r]) * inv_norm2[r]) * mphi[r];
+        for (int r = 0; r < 3; ++r)
+            c[r] += t.hn[r] * (t.Gx[r] * xfx + t.Gy[r] * yfy - t.GA[r] * uf);
+        c[3] += t.hn[3] * (t.B[0] * m.fx);
+        c[4] += t.hn[4] * (t.B[1] * m.fx);
+        c[5] += t.hn[5] * (t.B[2] * m.fy);
+        c[6] += t.hn[6] * (t.B[3] * m.fy);
+        c[7] += t.hn[7] * (2.0 * (t.Q7x * xfx + t.Q7y * yfy));
+        c[8] += t.hn[8] * (t.Q8 * (ux * m.fy + uy * m.fx));
     }
     double dv[Q];
     mrt_backward(c, dv);
 #pragma unroll
     for (int k = 0; k < Q; ++k) g[k] = f[k] + dv[k];
+    return m;
 }
 
 // MRT with the reference's rates S = (1, 1, 1, 1, 1, 1, 1, s7, s8)
@@ -311,11 +344,12 @@ __device__ __forceinline__ Moments collide(const KParams &p, const double f[Q],
 {
     if constexpr (COLL == 2) {
         return collide_mrt_stress<FORCING>(p, f, g);
+    } else if constexpr (COLL == 1) {
+        return collide_mrt_moments<FORCING>(p, f, g);
     } else {
         const Moments m = moments(p, f);
         const double u2 = m.ux * m.ux + m.uy * m.uy;
-        if constexpr (COLL == 0) bgk_all<FORCING>(p, m, u2, f, g);
-        else mrt_all<FORCING>(p, m, u2, f, g);
+        bgk_all<FORCING>(p, m, u2, f, g);
         return m;
     }
 }

@@ -42,12 +42,32 @@ struct MrtStress {
     double k2cg[4];      // k2 * (c . g)
 };
 
+// Nine-rate MRT in moment space (collide_mrt_moments in plb_collide.cuh): the
+// moments of the second-order equilibrium and of the Guo source are
+// polynomials in (rho, u, F) whose coefficients are lattice sums of the rows
+// of M against the weights -- computed once on the host from the caller's own
+// w / inv_cs_2 / inv_cs_4 (so that nothing assumes cs^2 = 1/3 exactly).
+//   rows 0-2 (rho, e, eps):  m_eq = rho (A + Qx ux^2 + Qy uy^2)
+//                            m_F  = -GA (u.F) + Gx ux Fx + Gy uy Fy
+//   rows 3-6 (jx, qx, jy, qy): m_eq = rho B u_a,  m_F = B F_a   (a = x, x, y, y)
+//   row 7 (pxx): m_eq = rho (Q7x ux^2 + Q7y uy^2),  m_F = 2 (Q7x ux Fx + Q7y uy Fy)
+//   row 8 (pxy): m_eq = rho Q8 ux uy,               m_F = Q8 (ux Fy + uy Fx)
+struct MrtMoments {
+    double A[3], Qx[3], Qy[3];
+    double GA[3], Gx[3], Gy[3];
+    double B[4];
+    double Q7x, Q7y, Q8;
+    double sn[Q];        // s_r / |row r|^2
+    double hn[Q];        // (1 - s_r / 2) / |row r|^2
+};
+
 struct KParams {
     Layout L;
     double omega, gx, gy, inv_cs_2, inv_cs_4, eps;
     double w[Q];
     double s[Q];   // MRT relaxation rates
     MrtStress mrt;
+    MrtMoments mrtm;
 };
 
 // Node classes in the code plane.

@@ -78,13 +78,13 @@ __host__ __device__ constexpr bool bulk_speculate(int coll)
 // occupancy, so registers are capped as low as each instantiation allows
 // without spilling (measured on B200, profiles/r01_occupancy_sweep.txt:
 // 6 CTAs x 128 threads = 80 registers reaches the measured copy bandwidth;
-// the Guo second-order MRT kernel needs 96 registers, the nine-rate MRT 120).
+// the Guo second-order MRT kernel needs 96 registers, the nine-rate MRT in moment space 94 at 5 CTAs).
 __host__ __device__ constexpr int bulk_min_blocks(int coll, int forcing)
 {
 #ifdef PLB_MINBLOCKS
     return PLB_MINBLOCKS;
 #else
-    return coll == 1 ? 4 : 6;
+    return coll == 1 ? 5 : 6;
 #endif
 }
 
@@ -379,6 +379,12 @@ __host__ __device__ constexpr int fused_smem_bytes(int depth)
 // Resident CTAs per SM asked of ptxas, per collision model (PLB_FUSED_MINBLOCKS
 // for all, PLB_FUSED_MINBLOCKS_BGK for the reference-ordered BGK kernels, which
 // need more registers than the two-stress-moment MRT).
+#ifndef PLB_FUSED_BULK_FENCE
+#define PLB_FUSED_BULK_FENCE 1
+#endif
+#ifndef PLB_FUSED_BULK_LATE
+#define PLB_FUSED_BULK_LATE 0
+#endif
 #ifndef PLB_FUSED_MINBLOCKS_D3
 #define PLB_FUSED_MINBLOCKS_D3 (256 / PLB_FUSED_BLOCK)
 #endif
@@ -459,6 +465,15 @@ __device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned 
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(d), "l"(gmem), "r"(bytes), "r"(b)
         : "memory");
+#endif
+}
+// Orders this thread's earlier generic-proxy accesses to shared memory (the
+// ld.shared of a ring slot) before later async-proxy accesses (the bulk copy
+// that refills the slot).
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+#ifndef PLB_EMU_RUNTIME
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
 }
 // Waits for the phase of `bar` with the given parity.  A copy that never
@@ -609,6 +624,14 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         // row number j of this item into its slot, which every lane has just
         // read into registers (__syncwarp: those reads are done)
         auto fill = [&](int j) {
+            // The slot is rewritten by the async proxy (TMA) right after the
+            // generic-proxy reads above: the cross-proxy fence orders every
+            // lane's reads before the copy that lane 0 issues after the warp
+            // barrier.  (Without it the round-2 hardware sweep produced
+            // run-to-run different fields; the host emulation cannot see this.)
+#if PLB_FUSED_BULK_FENCE
+            fence_proxy_async_smem();
+#endif
             __syncwarp();
             if (lane == 0 && run_bytes != 0 && j < n_rows) {
                 const unsigned g = filled + unsigned(j);
@@ -667,7 +690,9 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
                     fa[k] = v.x;
                     fb[k] = v.y;
                 }
+#if !PLB_FUSED_BULK_LATE
                 fill(i + AHEAD);            // the same slot, AHEAD rows on
+#endif
             }
 #elif PLB_FUSED_STAGES >= 2
             {
@@ -705,6 +730,11 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
                 if (!complete) break;
                 double sa[Q], sb[Q];
                 fused_stage1<COLL, FORCING>(a, fa, fb, sa, sb);
+#if PLB_FUSED_BULK && PLB_FUSED_BULK_LATE
+                // refill only after the row has been collided: its values have
+                // then provably left shared memory (data dependence)
+                if (l == 0) fill(i + AHEAD);
+#endif
 #if PLB_FUSED_CARRY_SMEM
                 {
                     double2(*c)[PLB_FUSED_BLOCK] = carry_s[l];

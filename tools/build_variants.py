@@ -59,6 +59,18 @@ VARIANTS = {
                        "-DPLB_FUSED_BLOCK=64", "-DPLB_FUSED_MINBLOCKS=10",
                        "-DPLB_FUSED_MINBLOCKS_D3=8"],
     "bulk_s1": ["-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=1"],
+    # round 2: the TMA ring raced on hardware (slot refilled by the async proxy
+    # right after the generic-proxy reads).  fence = cross-proxy fence before
+    # the refill (now the default), late = refill after the row was collided.
+    "cb_s1_mb5_late": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=1",
+                       "-DPLB_FUSED_MINBLOCKS=5", "-DPLB_FUSED_MINBLOCKS_D3=4",
+                       "-DPLB_FUSED_BULK_LATE=1"],
+    "cb_s1_mb5_nofence_late": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1",
+                               "-DPLB_FUSED_STAGES=1", "-DPLB_FUSED_MINBLOCKS=5",
+                               "-DPLB_FUSED_MINBLOCKS_D3=4", "-DPLB_FUSED_BULK_LATE=1",
+                               "-DPLB_FUSED_BULK_FENCE=0"],
+    "cb_s1_mb5_d3mb5": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=1",
+                        "-DPLB_FUSED_MINBLOCKS=5", "-DPLB_FUSED_MINBLOCKS_D3=5"],
 }
 
 if __name__ == "__main__":
