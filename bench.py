@@ -453,13 +453,18 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device,
 
     factory, nx, ny, scaling, text = workload_sizes(workload, world, scale)
     sim = factory(nx, ny, world, steps)
+    t_setup = time.perf_counter()
     solver = Solver(comm, "b200", simulation=sim, device=device, verbose=False)
     st = solver.state
     total_nodes = nx * ny
-    t_setup = time.perf_counter()
+    t_backend = time.perf_counter()
     solver.set_backend()
     solver.compile()
-    setup_s = time.perf_counter() - t_setup
+    # wall clock of the setup a user waits for: host containers (State: flags,
+    # link lists, initial fields), then device allocation + uploads + node
+    # classification (set_backend)
+    setup_s = {"host_state": t_backend - t_setup,
+               "set_backend": time.perf_counter() - t_backend}
     plb = solver.plb
     info = plb.info()
 

@@ -165,9 +165,9 @@ struct plb_solver {
 
     // Several steps per pass (step_fused): PLB_FUSE = 0 off, 1 when the
     // geometry qualifies (default), 2 whenever there is a deep node at all;
-    // PLB_FUSE_DEPTH = steps per pass (2, or 3: opt-in until measured).
+    // PLB_FUSE_DEPTH = steps per pass (3 by default since round 2; 2).
     int fuse_mode = PLB_FUSE_DEFAULT;
-    int fuse_depth = 2;
+    int fuse_depth = 3;
     int fused_depth_ok = 0;              // largest depth the geometry qualifies for (0: none)
     double *f_mid[2] = {nullptr, nullptr};   // compact scratch lattices (lazy)
     // node index -> compact scratch lattice, one entry per 16 nodes (lat_off);
@@ -181,7 +181,9 @@ struct plb_solver {
     LinkNode *lists_dev[2][3] = {};
     int64_t n_lists[2][3] = {};
     int64_t n_deep[2] = {0, 0};          // nodes the depth-2 / depth-3 kernel advances
-    int32_t fused_rows = 32;             // rows a warp marches over (PLB_FUSED_ROWS)
+    // rows a warp marches over per work item, for two / three steps per pass
+    // (PLB_FUSED_ROWS sets both)
+    int32_t fused_rows[2] = {32, 64};
     unsigned *work_counter = nullptr;    // PLB_FUSED_DYNAMIC=1: persistent grid, work queue
     int64_t pending = 0;                 // plain steps held back for grouping
     int64_t groups_done[2] = {0, 0};
@@ -647,7 +649,7 @@ int step_fused(plb_solver *s, int depth)
     // of running beside it: between ranks the grid is always the plain one.
     unsigned *work_counter = s->comm ? nullptr : s->work_counter;
     s->launches += launch_bulk_fused(a, s->deep_dev, depth, depth - 2, L.nx - (depth - 2),
-                                     s->fused_rows, work_counter, s->stream);
+                                     s->fused_rows[depth - 2], work_counter, s->stream);
     if (prof) {
         CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used + 1], s->stream));
         s->prof_used += 2;
@@ -928,7 +930,7 @@ int plb_create(const plb_config *c, plb_handle *out)
     if (const char *v = getenv("PLB_FUSE")) s->fuse_mode = atoi(v);
     if (s->fuse_mode < 0 || s->fuse_mode > 2) s->fuse_mode = PLB_FUSE_DEFAULT;
     if (const char *v = getenv("PLB_FUSE_DEPTH")) s->fuse_depth = atoi(v);
-    if (s->fuse_depth < 2 || s->fuse_depth > 3) s->fuse_depth = 2;
+    if (s->fuse_depth < 2 || s->fuse_depth > 3) s->fuse_depth = 3;
     s->kernel_collision = c->collision;
     if (c->collision == PLB_MRT) {
         // S = (1,..,1,s7,s8) as in base/collision_operator.py:159-163 needs
@@ -1366,14 +1368,17 @@ int plb_finalize_geometry(plb_handle s)
             CUDA_TRY(cudaMalloc(&s->deep_dev, deep.size()));
             CUDA_TRY(cudaMemcpy(s->deep_dev, deep.data(), deep.size(), cudaMemcpyHostToDevice));
             if (const char *v = getenv("PLB_FUSED_ROWS")) {
-                s->fused_rows = std::max(1, atoi(v));
+                s->fused_rows[0] = s->fused_rows[1] = std::max(1, atoi(v));
             } else {
-                // Short chunks measured best on B200 (profiles/: 32 rows beat 76,
-                // 128 and 512 although 2 of 34 row loads are then redundant):
-                // more warps are in their prologue at any time, which puts more
-                // loads in flight.  Small lattices: >= 4 waves.
+                // Chunk height measured on B200 (profiles/): two steps per pass:
+                // 32 rows beat 64 / 128 / 512 although 2 of 34 row loads are
+                // then redundant (more warps in their prologue at any time =
+                // more loads in flight); three steps per pass: 64 rows (4 of 68
+                // redundant) beat 32 and tie with 128.  Small lattices: >= 4
+                // waves of work items.
                 const int64_t want = nx * fused_strips(L, 2) / (148 * 16 * 4);
-                s->fused_rows = int32_t(std::min<int64_t>(32, std::max<int64_t>(8, want)));
+                s->fused_rows[0] = int32_t(std::min<int64_t>(32, std::max<int64_t>(8, want)));
+                s->fused_rows[1] = int32_t(std::min<int64_t>(64, std::max<int64_t>(8, want)));
             }
         }
     }
@@ -1534,7 +1539,7 @@ int plb_fused_info(plb_handle s, int64_t out[8])
     out[2] = s->n_deep[1];
     out[3] = d >= 2 ? s->n_lists[d - 2][0] : 0;
     out[4] = s->groups_done[0];
-    out[5] = s->fused_rows;
+    out[5] = s->fused_rows[d >= 3 ? 1 : 0];
     out[6] = fused_strips(s->L, d >= 2 ? d : 2);
     out[7] = s->groups_done[1];
     return PLB_OK;

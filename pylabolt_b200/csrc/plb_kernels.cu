@@ -318,46 +318,54 @@ __host__ __device__ constexpr int fused_span(int depth) { return 64 - 2 * (depth
 #ifndef PLB_FUSED_BLOCK
 #define PLB_FUSED_BLOCK 128
 #endif
-// Three CTAs of 128 threads per SM: 168 registers, nothing spills.  Measured on
-// B200 (profiles/r01_fused_sweep_v3_deepflags.txt): 82.0 GLUPS (MRT + Guo) /
-// 81.7 (BGK) against 70 / 64 at four CTAs (128 registers, spills in the loop)
-// and 52 at five; without the prefetch ring 12 warps would not hide the
-// row-load latency, with it they do.
+// Shipped configuration since round 2 (profiles/r02_fused_sweep_*.txt, 4096 x
+// 16384 sweep lattice, MRT + Guo / BGK):
+//   * the carried populations live in shared memory (PLB_FUSED_CARRY_SMEM), which
+//     takes three steps per pass from 200 to ~130 registers;
+//   * the row ring is ONE slot per warp filled by the TMA unit (PLB_FUSED_BULK,
+//     PLB_FUSED_STAGES = 1): refilled as soon as it has been read, it still
+//     fetches one row ahead, needs no destination registers and no LSU
+//     instruction in 31 of 32 lanes;
+//   * three 128-thread CTAs per SM for three steps per pass (55 KB of shared
+//     memory each), four for two steps per pass.
+// Three steps per pass: 109.0 / 96.3 GLUPS; the same with a cp.async ring of
+// two slots 103.9 / 92.4; carry in registers (200 registers, 8 warps) 88.6 /
+// 80.5; round 1's two-step kernel (registers, cp.async ring) 82.2 / 81.5.
 #ifndef PLB_FUSED_MINBLOCKS
-#define PLB_FUSED_MINBLOCKS 3
+#define PLB_FUSED_MINBLOCKS 4
 #endif
-// Row prefetch ring.  At 128 registers only 16 warps fit on an SM and ncu shows
-// them waiting on their row loads (long scoreboard: 6 of 10 cycles per issue),
-// so the rows are fetched AHEAD of their use with cp.async into a per-lane
-// shared-memory ring -- asynchronous copies need no destination registers.
-// PLB_FUSED_STAGES = slots of the ring (rows in flight + the one in use);
-// 0 = plain loads.  Every lane copies and later reads only its own 16 bytes
-// per population, so the ring needs no barrier, only cp.async.wait_group.
+// Row prefetch ring.  Warps wait on their row loads (round-1 ncu: long
+// scoreboard 6 of 10 cycles per issue), so rows are fetched AHEAD of their use
+// into a per-warp shared-memory ring -- asynchronous copies need no
+// destination registers.  PLB_FUSED_STAGES = slots of the ring; 0 = plain loads.
+// Every lane reads only its own 16 bytes per population, so the ring needs no
+// block barrier.
 #ifndef PLB_FUSED_STAGES
-#define PLB_FUSED_STAGES 2
+#define PLB_FUSED_STAGES 1
 #endif
-// PLB_FUSED_BULK=1 (tuning variant): the ring is filled by the TMA unit instead
-// of per-lane cp.async -- a warp's row is nine contiguous runs of 512 bytes, so
-// one elected lane issues nine cp.async.bulk copies that complete on a
-// per-warp, per-slot mbarrier (no LSU instruction, no address arithmetic in
-// the other 31 lanes).  Here a slot is refilled right after it has been read
-// into registers, so PLB_FUSED_STAGES slots keep that many rows in flight and
-// a single slot (18 KB per CTA) already fetches one row ahead.
+// PLB_FUSED_BULK=1: the ring is filled by the TMA unit -- a warp's row is nine
+// contiguous runs of 512 bytes, so one elected lane issues nine cp.async.bulk
+// copies (SASS UBLKCP) that complete on a per-warp, per-slot mbarrier.  A slot
+// is refilled right after it has been read into registers (behind a
+// cross-proxy fence, see fill()), so PLB_FUSED_STAGES slots keep that many rows
+// in flight and a single slot (18 KB per CTA) already fetches one row ahead.
+// PLB_FUSED_BULK=0: per-lane cp.async.cg copies (needs PLB_FUSED_STAGES >= 2).
 #ifndef PLB_FUSED_BULK
-#define PLB_FUSED_BULK 0
+#define PLB_FUSED_BULK 1
 #endif
 #if PLB_FUSED_BULK && PLB_FUSED_STAGES < 1
 #error "PLB_FUSED_BULK needs a ring (PLB_FUSED_STAGES >= 1)"
 #endif
-// PLB_FUSED_CARRY_SMEM=1 (tuning variant): the post-collision populations that
-// wait one or two iterations for their row (FusedCarry: 18 doubles per lane and
-// level) live in shared memory instead of registers -- every lane reads and
-// writes only its own 16-byte slots, once per iteration, so no barrier is
-// needed and the accesses are conflict free.  Frees ~36 registers per level:
-// two steps per pass then fit 128 registers (four CTAs per SM), three steps
-// per pass 168 (three CTAs per SM).
+#if !PLB_FUSED_BULK && PLB_FUSED_STAGES == 1
+#error "a cp.async ring needs two slots (PLB_FUSED_STAGES >= 2), or none (0)"
+#endif
+// PLB_FUSED_CARRY_SMEM=1: the post-collision populations that wait one or two
+// iterations for their row (FusedCarry: 18 doubles per lane and level) live in
+// shared memory instead of registers -- every lane reads and writes only its
+// own 16-byte slots, once per iteration, so no barrier is needed and the
+// accesses are conflict free.  Frees ~36 registers per level.
 #ifndef PLB_FUSED_CARRY_SMEM
-#define PLB_FUSED_CARRY_SMEM 0
+#define PLB_FUSED_CARRY_SMEM 1
 #endif
 // Shared memory of one CTA of k_bulk_fused<.., DEPTH>: the ring, the carried
 // populations of DEPTH - 1 levels, the ring's mbarriers.  The shipped build (ring
@@ -386,12 +394,12 @@ __host__ __device__ constexpr int fused_smem_bytes(int depth)
 #define PLB_FUSED_BULK_LATE 0
 #endif
 #ifndef PLB_FUSED_MINBLOCKS_D3
-#define PLB_FUSED_MINBLOCKS_D3 (256 / PLB_FUSED_BLOCK)
+#define PLB_FUSED_MINBLOCKS_D3 (384 / PLB_FUSED_BLOCK)
 #endif
 __host__ __device__ constexpr int fused_min_blocks(int coll, int depth)
 {
-    // three steps carry 36 doubles per lane (198 registers for MRT + Guo):
-    // 256 threads per SM unless told otherwise
+    // three steps per pass: 384 threads per SM (168 registers allowed, ~130
+    // used with the carry in shared memory; four CTAs measured 1 % slower)
     if (depth >= 3) return PLB_FUSED_MINBLOCKS_D3;
 #ifdef PLB_FUSED_MINBLOCKS_BGK
     return coll == 0 ? PLB_FUSED_MINBLOCKS_BGK : PLB_FUSED_MINBLOCKS;

@@ -53,10 +53,10 @@ def check_base(line):
 
 
 def test_own_arm_line():
-    line = run_bench("--scale", "0.02", "--steps", "9", "--warmup", "3",
+    line = run_bench("--scale", "0.02", "--steps", "11", "--warmup", "3",
                      "--cpu-sample", "128")
     check_base(line)
-    assert line["n_gpus"] == 1 and line["steps"] == 9 and line["warmup"] == 3
+    assert line["n_gpus"] == 1 and line["steps"] == 11 and line["warmup"] == 3
     assert line["scaling"] == "weak"
     assert "MRT" in line["config"]["workload"] and "channel" in line["config"]["workload"]
     roof = line["roofline"]
@@ -64,10 +64,11 @@ def test_own_arm_line():
         assert key in roof, key
     assert roof["bound"] == "hbm" and roof["unit"] == "GB/s"
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
-    # nine steps = four two-step passes + one single step, all counted
+    # eleven steps = three three-step passes + one two-step pass, all counted
     reps = line["repeats"]
     assert reps >= 1 and len(line["repeat_ms"]) == reps
-    assert roof["pairs"] == 4 * reps and roof["single_steps"] == reps and roof["triples"] == 0
+    assert roof["triples"] == 3 * reps and roof["pairs"] == reps and roof["single_steps"] == 0
+    assert roof["steps_per_launch"] == 3 and line["config"]["steps_per_pass"] == 3
     assert roof["frac"] <= roof["step_equivalent_frac"]
     assert "fused: block=" in roof["kernel_build"]
     assert line["gpu_launches"] > 0
@@ -80,19 +81,19 @@ def test_own_arm_line():
     par = line["parity"]
     assert par["ok"] is True and par["max_rel_err"] <= 1e-12
     assert par["e2e_max_rel_err"] <= 1e-12
-    assert par["steps_compared"] == 3 + 9 * reps + 1
+    assert par["steps_compared"] == 3 + 11 * reps + 1
     # configs[3] rides along, with its own parity
     assert "cavity" in line["extra"] and "cavity_16384_bgk" in line
     assert line["extra"]["cavity"]["parity"]["ok"] is True
     assert line["extra"]["cavity"]["scaling"] == "strong"
 
 
-def test_depth_three_is_accounted_for():
+def test_two_steps_per_pass_are_accounted_for():
     env_key = "PLB_FUSE_DEPTH"
     old = os.environ.get(env_key)
-    os.environ[env_key] = "3"
+    os.environ[env_key] = "2"
     try:
-        line = run_bench("--scale", "0.02", "--steps", "11", "--warmup", "3",
+        line = run_bench("--scale", "0.02", "--steps", "9", "--warmup", "3",
                          "--no-extras", "--no-cpu-baseline")
     finally:
         if old is None:
@@ -101,9 +102,9 @@ def test_depth_three_is_accounted_for():
             os.environ[env_key] = old
     roof = line["roofline"]
     reps = line["repeats"]
-    assert roof["triples"] == 3 * reps and roof["pairs"] == reps and roof["single_steps"] == 0
+    assert roof["pairs"] == 4 * reps and roof["single_steps"] == reps and roof["triples"] == 0
     assert line["parity"]["ok"] is True
-    assert roof["steps_per_launch"] == 3 and line["config"]["steps_per_pass"] == 3
+    assert roof["steps_per_launch"] == 2 and line["config"]["steps_per_pass"] == 2
     assert line["cpu_baseline"] is None
 
 

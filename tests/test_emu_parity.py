@@ -41,7 +41,9 @@ def emu(emu_lib, monkeypatch):
     monkeypatch.setenv("PLB_LIB", emu_lib)
     monkeypatch.setattr(capi, "_accept_emulated_build", True)
     monkeypatch.delenv("PLB_FUSED_ROWS", raising=False)
-    monkeypatch.delenv("PLB_FUSE_DEPTH", raising=False)
+    # the pair-counting tests below pin two steps per pass; the shipped
+    # default (three) has its own tests and test_default_is_three_steps_per_pass
+    monkeypatch.setenv("PLB_FUSE_DEPTH", "2")
     monkeypatch.delenv("PLB_EMU_BLOCK_ORDER", raising=False)
     monkeypatch.delenv("PLB_FUSED_DYNAMIC", raising=False)
     monkeypatch.delenv("PLB_KERNEL", raising=False)
@@ -271,6 +273,29 @@ def test_default_mode_pairs_only_where_deep_nodes_dominate(emu):
     finally:
         small.close()
         large.close()
+
+
+def test_default_is_three_steps_per_pass(emu):
+    """Shipped default since round 2: plain steps go three at a time, a
+    remainder of two as a pair, a single one through the single-step kernel."""
+    emu.delenv("PLB_FUSE", raising=False)
+    emu.delenv("PLB_FUSE_DEPTH", raising=False)
+    factory = lambda: cases.cavity(201, 201)
+    s = make_solver(factory())
+    try:
+        info = s.plb.fused_info()
+        assert info["active"] == 3 and info["n_deep3"] == 195 * 195
+        s.advance(11)
+        s.plb.sync()
+        info = s.plb.fused_info()
+        assert info["triples"] == 3 and info["pairs"] == 1
+        s.advance(1, store_moments_last=True)
+        got = s.fields_to_host()
+    finally:
+        s.close()
+    want, _ = _run(factory, 12, "0", emu)
+    for key in ("density", "velocity", "pop_fluid_new"):
+        assert np.array_equal(got[key], want[key]), key
 
 
 def test_held_back_step_is_completed_by_every_observer(emu):

@@ -23,6 +23,14 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-12
 
 
+@pytest.fixture(autouse=True)
+def two_steps_per_pass(monkeypatch):
+    """This module counts PAIRS: it pins two steps per pass.  The shipped
+    default (three, since round 2) is covered by test_gpu_zz_fused_depth3.py,
+    the full-size tests and every other GPU module."""
+    monkeypatch.setenv("PLB_FUSE_DEPTH", "2")
+
+
 def _fields(sim_factory, n_steps, fuse, strict, monkeypatch, one_by_one=False,
             depth=2):
     monkeypatch.setenv("PLB_FUSE", fuse)

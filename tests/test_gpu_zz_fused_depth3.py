@@ -1,7 +1,6 @@
-"""PLB_FUSE_DEPTH=3 on the GPU: three steps per pass (opt-in until it has been
-timed).  Same kernel template as the two-step path, one
-hand-over deeper.  Kept in its own module, collected after the other GPU
-modules, because these cases had not run on a B200 when round 1 ended.
+"""Three steps per pass on the GPU (the shipped default since round 2;
+DESIGN.md section 3a).  Same kernel template as the two-step path, one
+hand-over deeper.
 """
 import numpy as np
 import pytest
@@ -14,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("name", sorted(WIDE_CASES))
 def test_three_steps_per_pass_equals_single_steps(name, monkeypatch):
-    """PLB_FUSE_DEPTH=3 (opt-in): 14 plain steps = 4 triples + 1 pair."""
+    """14 plain steps = 4 triples + 1 pair."""
     factory = WIDE_CASES[name]
     want, _ = _fields(factory, 15, "0", True, monkeypatch)
     got, info = _fields(factory, 15, "2", True, monkeypatch, depth=3)
@@ -30,5 +29,28 @@ def test_three_steps_per_pass_mid_size(name, monkeypatch):
     want, _ = _fields(factory, 21, "0", True, monkeypatch)
     got, info = _fields(factory, 21, "1", True, monkeypatch, depth=3)
     assert info["active"] == 3 and info["triples"] == 6 and info["pairs"] == 1
+    for key in ("density", "velocity", "pop_fluid_new"):
+        assert np.array_equal(got[key], want[key]), key
+
+
+def test_default_is_three_steps_per_pass(monkeypatch):
+    """No environment at all: the library groups plain steps three at a time
+    and the result is that of single steps, bit for bit (strict build)."""
+    monkeypatch.delenv("PLB_FUSE_DEPTH", raising=False)
+    monkeypatch.delenv("PLB_FUSE", raising=False)
+    from test_gpu_parity import make_solver
+    factory = MID_CASES["channel_mrt_guo2_900x1300"]
+    s = make_solver(factory(), strict=True)
+    try:
+        assert s.plb.fused_info()["active"] == 3
+        s.advance(20)
+        s.advance(1, store_moments_last=True)
+        info = s.plb.fused_info()
+        assert info["triples"] == 6 and info["pairs"] == 1
+        got = s.fields_to_host()
+        assert "ring=tma-bulk carry=shared" in s.plb.build_info()
+    finally:
+        s.close()
+    want, _ = _fields(factory, 21, "0", True, monkeypatch)
     for key in ("density", "velocity", "pop_fluid_new"):
         assert np.array_equal(got[key], want[key]), key
