@@ -128,6 +128,14 @@ int plb_finalize_geometry(plb_handle h);
 int plb_upload(plb_handle h, int32_t field, const void *host, size_t bytes);
 int plb_download(plb_handle h, int32_t field, void *host, size_t bytes);
 
+/* A uniform field without a host array: PLB_DENSITY (value[0]) or PLB_VELOCITY
+ * (value[0], value[1]) on every interior node, 0 on the ghost ring -- what
+ * set_field_scalar / set_field_vector (pylabolt/base/init_fields.py:325-375)
+ * leave behind for a `type: "fixed"` entry of initial_fields_dict, produced on
+ * the device instead of being copied over PCIe.  Solid nodes carry the body's
+ * own density / velocity in the reference; a case with obstacles uploads. */
+int plb_fill(plb_handle h, int32_t field, const double *value);
+
 /* f = f_eq(rho, u) on fluid nodes, 0 elsewhere: CollisionOperator.initialize_pop,
  * pylabolt/parallel/cpu/equilibrium_kernels.py:38-78. */
 int plb_initialize_pop(plb_handle h);

@@ -24,7 +24,7 @@ BC_TYPE = {"bounce_back": 0, "fixed_velocity": 1, "fixed_pressure": 2,
 EXPORTS = [
     "plb_create", "plb_destroy", "plb_last_error",
     "plb_add_boundary_element", "plb_finalize_geometry",
-    "plb_upload", "plb_download", "plb_initialize_pop",
+    "plb_upload", "plb_download", "plb_fill", "plb_initialize_pop",
     "plb_step", "plb_sync", "plb_residue_sums",
     "plb_comm_unique_id", "plb_comm_init",
     "plb_event_record", "plb_event_elapsed_ms", "plb_kernel_launches",
@@ -93,6 +93,7 @@ def load_library(strict=None):
     lib.plb_finalize_geometry.argtypes = [vp]
     lib.plb_upload.argtypes = [vp, i32, vp, ctypes.c_size_t]
     lib.plb_download.argtypes = [vp, i32, vp, ctypes.c_size_t]
+    lib.plb_fill.argtypes = [vp, i32, ctypes.POINTER(dbl)]
     lib.plb_initialize_pop.argtypes = [vp]
     lib.plb_step.argtypes = [vp, i64, i32]
     lib.plb_sync.argtypes = [vp]
@@ -256,6 +257,13 @@ class Plb:
         a = np.ascontiguousarray(array, dtype=dtype)
         self._check(self.lib.plb_upload(self._h, field, a.ctypes.data,
                                         a.nbytes))
+
+    def fill(self, field, value):
+        """Uniform DENSITY (scalar) / VELOCITY (pair) on the interior nodes,
+        produced on the device (plb_fill)."""
+        vals = np.atleast_1d(np.asarray(value, dtype=np.float64))
+        buf = (ctypes.c_double * 2)(*(list(vals) + [0.0])[:2])
+        self._check(self.lib.plb_fill(self._h, field, buf))
 
     def download(self, field, out=None):
         shapes = {SOLID: ((self.size,), np.uint8),

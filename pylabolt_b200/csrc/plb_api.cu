@@ -1461,6 +1461,27 @@ int plb_upload(plb_handle s, int32_t field, const void *host, size_t bytes)
     }
 }
 
+int plb_fill(plb_handle s, int32_t field, const double *value)
+{
+    if (!s || !value) return fail(PLB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    if (int rc = flush_pending(s)) return rc;
+    switch (field) {
+    case PLB_DENSITY:
+        s->launches += launch_fill_inner(s->L, s->rho(), value[0], s->stream);
+        break;
+    case PLB_VELOCITY:
+        s->launches += launch_fill_inner(s->L, s->ux(), value[0], s->stream);
+        s->launches += launch_fill_inner(s->L, s->uy(), value[1], s->stream);
+        break;
+    default:
+        return fail(PLB_ERR_INVALID, "plb_fill: field %d is not PLB_DENSITY / "
+                    "PLB_VELOCITY", field);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PLB_OK;
+}
+
 int plb_download(plb_handle s, int32_t field, void *host, size_t bytes)
 {
     if (!s || !host) return fail(PLB_ERR_INVALID, "null argument");

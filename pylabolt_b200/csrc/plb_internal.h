@@ -202,5 +202,7 @@ int launch_residue(const Layout &L, const uint8_t *code, const double *rho,
                    double *ux_old, double *uy_old, double *partials,
                    int n_blocks, double *out6, cudaStream_t stream);
 int launch_fill(double *buf, int64_t n, double value, cudaStream_t stream);
+// plane[node] = value on interior nodes, 0 on the ghost ring and the padding
+int launch_fill_inner(const Layout &L, double *plane, double value, cudaStream_t stream);
 
 }  // namespace plb

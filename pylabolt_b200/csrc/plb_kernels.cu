@@ -1165,6 +1165,16 @@ __global__ void k_fill(double *buf, int64_t n, double value)
         buf[i] = value;
 }
 
+__global__ void k_fill_inner(Layout L, double *plane, double value)
+{
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < L.plane;
+         i += stride) {
+        const int64_t x = i / L.pitch - 1, y = i % L.pitch - L.y0;
+        plane[i] = (x >= 0 && x < L.nx && y >= 0 && y < L.ny) ? value : 0.0;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
@@ -1441,6 +1451,12 @@ int launch_residue(const Layout &L, const uint8_t *code, const double *rho,
                uy, rho_old, ux_old, uy_old, partials);
     PLB_LAUNCH(SIMPLE, (k_residue_final), 1, 32, stream, partials, n_blocks, out6);
     return 2;
+}
+
+int launch_fill_inner(const Layout &L, double *plane, double value, cudaStream_t stream)
+{
+    PLB_LAUNCH(SIMPLE, (k_fill_inner), 148 * 8, 256, stream, L, plane, value);
+    return 1;
 }
 
 int launch_fill(double *buf, int64_t n, double value, cudaStream_t stream)

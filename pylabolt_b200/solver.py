@@ -139,8 +139,7 @@ class Solver:
             float_min=st.control.float_min, strict=self.backend.strict)
         plb = self.plb
         plb.upload(capi.SOLID, st.fields.solid)
-        plb.upload(capi.DENSITY, st.fields.density)
-        plb.upload(capi.VELOCITY, st.fields.velocity)
+        self.upload_initial_fields()
         for element in st.boundary.boundary_elements:
             plb.add_boundary_element(
                 element.type_fluid, element.boundary_nodes, element.out_list,
@@ -160,6 +159,44 @@ class Solver:
             self.momentum = MomentumExchange(st, plb.link_nodes())
         print_log("\nSetting simulation backend done!", rank, verbose)
         print_log("-" * 80, rank, verbose)
+
+    def _uniform_initial_value(self, key):
+        """The value of initial field ``key`` ("density" / "velocity") if the
+        case file fixes it to ONE value on every fluid node -- ``type: fixed``
+        in the default section, no region override -- and no obstacle writes
+        its own density / velocity into solid nodes; else None."""
+        if self.state.obstacle.obstacles:
+            return None
+        regions = getattr(self.simulation, "initial_fields_dict", {})
+        spec = regions.get("default", {}).get("fluid", {}).get(key)
+        if not isinstance(spec, dict) or spec.get("type") != "fixed":
+            return None
+        for name, user in regions.items():
+            if name != "default" and key in user.get("fluid", {}):
+                return None
+        return spec["value"]
+
+    def upload_initial_fields(self, density=None, velocity=None):
+        """fields.density / fields.velocity -> device (State.set_backend of
+        the reference mirrors every field array, base/fields.py:192-227).  A
+        field the case file fixes to one value everywhere is produced on the
+        device (plb_fill) instead of crossing PCIe as 8 (16) bytes per node;
+        everything else is uploaded from ``density`` / ``velocity`` (default:
+        the State's own arrays; a caller may pass pinned copies).  Returns
+        the bytes that crossed PCIe."""
+        st = self.state
+        moved = 0
+        for key, field, host in (("density", capi.DENSITY, density),
+                                 ("velocity", capi.VELOCITY, velocity)):
+            value = self._uniform_initial_value(key)
+            if value is not None:
+                self.plb.fill(field, value)
+                continue
+            if host is None:
+                host = getattr(st.fields, key)
+            self.plb.upload(field, host)
+            moved += host.nbytes
+        return moved
 
     # -- reference: Solver.single_time_step, fluidLB.py:206-253 ----------------
     def single_time_step(self, store_moments=False, record_links=False):

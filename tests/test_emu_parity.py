@@ -380,3 +380,26 @@ def test_fused_kernel_variants_equal_single_steps(emu, emu_variant_lib, name):
         assert info["pairs"] + info["triples"] > 0, info
         for key in ("density", "velocity", "pop_fluid_new"):
             assert np.array_equal(got[key], want[key]), (name, rows, depth, key)
+
+
+def test_uniform_initial_fields_are_filled_on_the_device(emu):
+    """A field the case file fixes to one value is produced by plb_fill; the
+    device then holds exactly what an upload of the host array would."""
+    sim = cases.cavity(40, 33)
+    sim.initial_fields_dict["default"]["fluid"]["velocity"]["value"] = [0.02, -0.01]
+    s = make_solver(sim)
+    try:
+        assert s._uniform_initial_value("density") == 1.0
+        assert s._uniform_initial_value("velocity") == [0.02, -0.01]
+        assert s.upload_initial_fields() == 0              # nothing crossed PCIe
+        assert np.array_equal(s.plb.download(capi.DENSITY), s.state.fields.density)
+        assert np.array_equal(s.plb.download(capi.VELOCITY), s.state.fields.velocity)
+    finally:
+        s.close()
+    body = make_solver(cases.cylinder())                  # a body: uploads
+    try:
+        assert body._uniform_initial_value("density") is None
+        assert body.upload_initial_fields() == (body.state.fields.density.nbytes +
+                                                body.state.fields.velocity.nbytes)
+    finally:
+        body.close()
