@@ -128,6 +128,8 @@ struct plb_solver {
     cudaEvent_t events[8] = {};
 
     double *f[2] = {nullptr, nullptr};   // two lattices, 9 planes each
+    TensorMap f_tmap[2];                 // their TMA descriptors (k_bulk_fused's row fetch)
+    bool tmap_ok = true;
     int cur = 0;
     double *mom = nullptr;               // rho, ux, uy planes
     double *mom_old = nullptr;           // residue field_old (lazy)
@@ -425,6 +427,12 @@ StepArgs step_args(const plb_solver *s, const double *fin, double *fout)
     a.store = 0;
     a.exch = nullptr;
     a.fin_plane = a.fout_plane = s->L.plane;
+    {
+        static const int cx[Q] = PLB_CX_LIST;
+        for (int k = 0; k < Q; ++k)
+            a.push_off[k] = (int64_t(k) * s->L.plane + cx[k] * s->L.pitch) *
+                            int64_t(sizeof(double));
+    }
     for (int m = 0; m < 2; ++m) {
         if (!s->f_mid[m]) continue;
         if (fin == s->f_mid[m]) {
@@ -649,7 +657,8 @@ int step_fused(plb_solver *s, int depth)
     // of running beside it: between ranks the grid is always the plain one.
     unsigned *work_counter = s->comm ? nullptr : s->work_counter;
     s->launches += launch_bulk_fused(a, s->deep_dev, depth, depth - 2, L.nx - (depth - 2),
-                                     s->fused_rows[depth - 2], work_counter, s->stream);
+                                     s->fused_rows[depth - 2], work_counter,
+                                     &s->f_tmap[s->cur], s->stream);
     if (prof) {
         CUDA_TRY(cudaEventRecord(s->prof_events[s->prof_used + 1], s->stream));
         s->prof_used += 2;
@@ -967,6 +976,14 @@ int plb_create(const plb_config *c, plb_handle *out)
     for (int i = 0; i < 2; ++i) {
         TRY_OR_CLEAN(cudaMalloc(&s->f[i], Q * plane_bytes));
         TRY_OR_CLEAN(cudaMemsetAsync(s->f[i], 0, Q * plane_bytes, s->stream));
+        if (fused_needs_tensor_map()) {
+            char why[200] = "";
+            if (make_lattice_tensor_map(&s->f_tmap[i], s->f[i], L, why, sizeof why)) {
+                // the single-step kernels need no descriptor: carry on with them
+                fprintf(stderr, "libplb: %s -- several steps per pass switched off\n", why);
+                s->tmap_ok = false;
+            }
+        }
     }
     TRY_OR_CLEAN(cudaMalloc(&s->mom, 3 * plane_bytes));
     TRY_OR_CLEAN(cudaMemsetAsync(s->mom, 0, 3 * plane_bytes, s->stream));
@@ -1309,7 +1326,7 @@ int plb_finalize_geometry(plb_handle s)
             }
             for (int64_t idx : lists[0]) on[size_t(idx)] = 0;   // clean for the next depth
             s->n_deep[depth - 2] = n_deep;
-            const bool ok = n_deep > 0 &&
+            const bool ok = n_deep > 0 && s->tmap_ok &&
                             (s->fuse_mode == 2 ||
                              (int64_t(lists[0].size()) * 8 <= n_fluid && n_fluid >= 4096));
             if (!ok) continue;

@@ -10,6 +10,8 @@
 // a signed zero are exact, so dropping those operations changes no bit (only,
 // possibly, the sign of an exact zero).
 #pragma once
+#include <cmath>
+
 #include "plb_internal.h"
 
 namespace plb {
@@ -42,6 +44,25 @@ __device__ __forceinline__ double cdot(double a, double b)
 struct Moments {
     double rho, ux, uy, fx, fy;
 };
+
+// 1 / x for the MRT paths (OUR DEFINITION, not bit-compared with upstream
+// code): the hardware seed (MUFU.RCP64H, ~2^-20) and two Newton steps -- four
+// DFMA, an error of an ulp, and none of the range checks and the slow-path
+// call an IEEE division carries (x = rho + eps is of order one).  The BGK
+// paths, which are pinned to the reference bit for bit, keep the division.
+__device__ __forceinline__ double rcp_newton(double x)
+{
+#ifdef PLB_EMU_RUNTIME
+    return 1.0 / x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#endif
+}
 
 // Phases 2-4 of Solver.single_time_step (pylabolt/solvers/fluidLB.py:211-224):
 //   rho = sum_k f_k, k = 0..8 in order   (cpu/compute_fields_kernels.py:24-28)
@@ -208,7 +229,7 @@ __device__ __forceinline__ Moments collide_mrt_moments(const KParams &p,
     m.rho = mom[0];
     m.fx = m.rho * p.gx;
     m.fy = m.rho * p.gy;
-    const double inv = 1.0 / (m.rho + p.eps);
+    const double inv = rcp_newton(m.rho + p.eps);
     // u = (sum_k c_k f_k + F/2) / rho, cpu/compute_fields_kernels.py:55-65
     m.ux = (mom[3] + 0.5 * m.fx) * inv;
     m.uy = (mom[5] + 0.5 * m.fy) * inv;
@@ -289,8 +310,10 @@ __device__ __forceinline__ void stress_pair(const KParams &p, double ux,
     }
     if constexpr (FORCING != 0) odd = p.inv_cs_2 * cu + p.mrt.k2cg[slot];
     else odd = p.inv_cs_2 * cu;
-    g[K] = wrho * (even + odd) + proj;
-    g[KI] = wrho * (even - odd) + proj;
+    // wrho (even +- odd) + proj as three fused multiply-adds
+    const double centre = fma(wrho, even, proj);
+    g[K] = fma(wrho, odd, centre);
+    g[KI] = fma(-wrho, odd, centre);
 }
 
 template <int FORCING>
@@ -307,7 +330,7 @@ __device__ __forceinline__ Moments collide_mrt_stress(const KParams &p,
     m.rho = ((f[0] + p13) + p24) + (p57 + p68);
     m.fx = m.rho * p.gx;
     m.fy = m.rho * p.gy;
-    const double inv = 1.0 / (m.rho + p.eps);
+    const double inv = rcp_newton(m.rho + p.eps);
     // u = (sum_k c_k f_k + F/2) / rho, cpu/compute_fields_kernels.py:55-65
     m.ux = (((d13 + d57) + d86) + m.rho * p.mrt.hgx) * inv;
     m.uy = (((d24 + d57) - d86) + m.rho * p.mrt.hgy) * inv;

@@ -134,6 +134,11 @@ struct StepArgs {
     // push_dst translate; the bulk kernels always work on full lattices.
     const int32_t *fin_map = nullptr, *fout_map = nullptr;
     int64_t fin_plane = 0, fout_plane = 0;
+    // Byte offset of the slot population k of a node is pushed into in a full
+    // lattice, without the c_y part: (k * plane + c_x[k] * pitch) * 8 -- nine
+    // loop-invariant 64-bit constants the fused kernel adds to its running row
+    // pointer straight from the constant bank.
+    int64_t push_off[Q] = {};
 };
 
 // node index -> offset inside one population plane of a (possibly compact) lattice
@@ -141,6 +146,21 @@ __host__ __device__ inline int64_t lat_off(const int32_t *map, int64_t idx)
 {
     return map ? ((int64_t(map[idx >> 4]) << 4) | (idx & 15)) : idx;
 }
+
+// A lattice as the TMA unit sees it: a rank-3 tensor of doubles, (column,
+// row, population) = (pitch, nx + 2, Q) with the strides of Layout.  128
+// opaque bytes (a CUtensorMap), 64-byte aligned, handed to the kernel as a
+// __grid_constant__ parameter.
+struct alignas(64) TensorMap {
+    unsigned long long opaque[16];
+};
+// Encodes the descriptor of `lattice` for boxes of (64 columns, 1 row, Q
+// populations); 0 on success, else a cudaError_t / CUresult-style code and a
+// message in `why`.
+int make_lattice_tensor_map(TensorMap *out, const double *lattice, const Layout &L,
+                            char *why, size_t why_len);
+// true if k_bulk_fused of this build fills its ring with tensor copies
+bool fused_needs_tensor_map();
 
 // ---- launchers implemented in plb_kernels.cu ---------------------------
 // All return the number of kernels launched (0 if nothing to do).
@@ -152,9 +172,13 @@ int launch_bulk(const StepArgs &a, int64_t x_begin, int64_t x_end, int variant,
 // neighbours are bulk nodes, capped at 2.
 // work_counter: null = one work item per warp; else a device word (zeroed by
 // the launcher) from which the warps of a persistent grid draw their items.
+// tmap: the TMA descriptor of lattice a.fin (make_lattice_tensor_map), through
+// which a warp fetches a whole row -- nine populations x 64 nodes -- with ONE
+// tensor copy; null only in builds whose ring is not tensor-filled.
 int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
                       int64_t x_begin, int64_t x_end, int32_t rows_per_chunk,
-                      unsigned *work_counter, cudaStream_t stream);
+                      unsigned *work_counter, const TensorMap *tmap,
+                      cudaStream_t stream);
 int fused_strips(const Layout &L, int depth);
 // compile-time configuration of the kernels (plb_build_info)
 const char *kernel_build_info();

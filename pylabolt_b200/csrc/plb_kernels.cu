@@ -20,8 +20,13 @@
 //                                 three populations that cross a face
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "plb_collide.cuh"
+#ifndef PLB_EMU_RUNTIME
+#include <cuda.h>            // CUtensorMap and its enums (no libcuda linkage)
+#endif
 
 // Every kernel launch goes through PLB_LAUNCH.  MODE documents (and, in the
 // host-side SIMT emulation used by tests/emu, selects) how the kernel's
@@ -115,6 +120,28 @@ __device__ __forceinline__ void st1(double *p, double a)
     __stcs(p, a);
 #else
     *p = a;
+#endif
+}
+// The pair (lo, hi) to p[0], p[1]: both halves (mode 3) as one 128-bit store,
+// one half (mode 1: lo, mode 2: hi) as a 64-bit store, nothing (mode 0) --
+// predicated, so that lanes with different modes do not diverge.
+__device__ __forceinline__ void st_pair(double *p, double lo, double hi, unsigned mode)
+{
+#if defined(PLB_EMU_RUNTIME) || PLB_ST_MODE == 1
+    if (mode == 3) st2(p, lo, hi);
+    else if (mode == 1) st1(p, lo);
+    else if (mode == 2) st1(p + 1, hi);
+#else
+    asm volatile(
+        "{\n\t.reg .pred both, only_lo, only_hi;\n\t"
+        "setp.eq.u32 both, %3, 3;\n\t"
+        "setp.eq.u32 only_lo, %3, 1;\n\t"
+        "setp.eq.u32 only_hi, %3, 2;\n\t"
+        "@both st.global.v2.f64 [%0], {%1, %2};\n\t"
+        "@only_lo st.global.f64 [%0], %1;\n\t"
+        "@only_hi st.global.f64 [%0+8], %2;\n\t}"
+        ::"l"(p), "d"(lo), "d"(hi), "r"(mode)
+        : "memory");
 #endif
 }
 
@@ -356,6 +383,16 @@ __host__ __device__ constexpr int fused_span(int depth) { return 64 - 2 * (depth
 #if PLB_FUSED_BULK && PLB_FUSED_STAGES < 1
 #error "PLB_FUSED_BULK needs a ring (PLB_FUSED_STAGES >= 1)"
 #endif
+// PLB_FUSED_TENSOR=1 (with PLB_FUSED_BULK): the lattice is described to the TMA
+// unit as a rank-3 tensor (column, row, population) and a warp's row -- a box
+// of 64 columns x 1 row x 9 populations -- is fetched by ONE
+// cp.async.bulk.tensor.3d (SASS UTMALDG) instead of nine linear bulk copies:
+// the nine-copy issue sequence was 185 of the ~1250 instructions a warp issues
+// per row (round-2 SASS, profiles/r02_sass_k_bulk_fused_mrt_guo2_depth3.txt),
+// executed by one lane.  Columns beyond the padded row are zero-filled by the
+// unit, which is what the lanes outside the row read before, too.  The box
+// lands densely, so a warp's ring slot is 9 x 512 contiguous bytes.
+// (Default below, once PLB_FUSED_CARRY_SMEM is known.)
 #if !PLB_FUSED_BULK && PLB_FUSED_STAGES == 1
 #error "a cp.async ring needs two slots (PLB_FUSED_STAGES >= 2), or none (0)"
 #endif
@@ -366,6 +403,15 @@ __host__ __device__ constexpr int fused_span(int depth) { return 64 - 2 * (depth
 // accesses are conflict free.  Frees ~36 registers per level.
 #ifndef PLB_FUSED_CARRY_SMEM
 #define PLB_FUSED_CARRY_SMEM 1
+#endif
+#ifndef PLB_FUSED_TENSOR
+#define PLB_FUSED_TENSOR (PLB_FUSED_BULK && PLB_FUSED_CARRY_SMEM)
+#endif
+#if PLB_FUSED_TENSOR && !PLB_FUSED_BULK
+#error "PLB_FUSED_TENSOR is a way of filling the PLB_FUSED_BULK ring"
+#endif
+#if PLB_FUSED_TENSOR && !PLB_FUSED_CARRY_SMEM
+#error "PLB_FUSED_TENSOR addresses the ring in dynamic shared memory (PLB_FUSED_CARRY_SMEM=1)"
 #endif
 // Shared memory of one CTA of k_bulk_fused<.., DEPTH>: the ring, the carried
 // populations of DEPTH - 1 levels, the ring's mbarriers.  The shipped build (ring
@@ -394,12 +440,12 @@ __host__ __device__ constexpr int fused_smem_bytes(int depth)
 #define PLB_FUSED_BULK_LATE 0
 #endif
 #ifndef PLB_FUSED_MINBLOCKS_D3
-#define PLB_FUSED_MINBLOCKS_D3 (384 / PLB_FUSED_BLOCK)
+#define PLB_FUSED_MINBLOCKS_D3 (512 / PLB_FUSED_BLOCK)
 #endif
 __host__ __device__ constexpr int fused_min_blocks(int coll, int depth)
 {
-    // three steps per pass: 384 threads per SM (168 registers allowed, ~130
-    // used with the carry in shared memory; four CTAs measured 1 % slower)
+    // three steps per pass: shared memory (55 KB per CTA) admits four CTAs of
+    // 128 threads per SM, i.e. 128 registers per thread
     if (depth >= 3) return PLB_FUSED_MINBLOCKS_D3;
 #ifdef PLB_FUSED_MINBLOCKS_BGK
     return coll == 0 ? PLB_FUSED_MINBLOCKS_BGK : PLB_FUSED_MINBLOCKS;
@@ -407,6 +453,12 @@ __host__ __device__ constexpr int fused_min_blocks(int coll, int depth)
     return PLB_FUSED_MINBLOCKS;
 #endif
 }
+
+#ifdef PLB_EMU_RUNTIME
+#define PLB_GRID_CONSTANT
+#else
+#define PLB_GRID_CONSTANT __grid_constant__
+#endif
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -475,6 +527,33 @@ __device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned 
         : "memory");
 #endif
 }
+// One box of (64 columns, 1 row, Q populations) of the lattice behind `map`,
+// first column c0 / row c1, into 9 x 512 dense bytes of shared memory.
+__device__ __forceinline__ void tensor_g2s(void *smem, const TensorMap *map, int c0,
+                                           int c1, unsigned long long *bar)
+{
+#ifdef PLB_EMU_RUNTIME
+    const double *base = reinterpret_cast<const double *>(map->opaque[0]);
+    const int64_t pitch = int64_t(map->opaque[1]), rows = int64_t(map->opaque[2]);
+    const int64_t plane = int64_t(map->opaque[3]);
+    double *dst = static_cast<double *>(smem);
+    for (int k = 0; k < Q; ++k)
+        for (int c = 0; c < 64; ++c) {
+            const int64_t col = int64_t(c0) + c;
+            const bool inside = col >= 0 && col < pitch && c1 >= 0 && c1 < rows;
+            dst[k * 64 + c] = inside ? base[k * plane + int64_t(c1) * pitch + col] : 0.0;
+        }
+    (void)bar;
+#else
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(d), "l"(map), "r"(c0), "r"(c1), "r"(0), "r"(b)
+        : "memory");
+#endif
+}
 // Orders this thread's earlier generic-proxy accesses to shared memory (the
 // ld.shared of a ring slot) before later async-proxy accesses (the bulk copy
 // that refills the slot).
@@ -507,19 +586,76 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 #endif
 }
 
+// PLB_FUSED_PIN=1: the collision constants a warp uses 3 x 2 times per row live in
+// registers for the whole kernel.  ptxas otherwise re-reads them from the
+// constant bank inside the loop (round-2 SASS: 130 LDC / LDCU of ~1070
+// instructions per row); the kernel's occupancy is set by its shared memory
+// (four CTAs of 55 KB), which leaves 128 registers per thread, 32 more than
+// the loop needs.  ptxas rematerialises anything it can trace back to the
+// constant bank (it even folds a warp shuffle of a uniform value), so the bit
+// pattern is XORed with a zero it cannot prove to be zero: bit 63 of the
+// cycle counter, read once per thread.
+#ifndef PLB_FUSED_PIN
+#define PLB_FUSED_PIN 1
+#endif
+__device__ __forceinline__ unsigned long long opaque_zero()
+{
+#ifdef PLB_EMU_RUNTIME
+    return 0;
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    return t >> 63;
+#endif
+}
+__device__ __forceinline__ void pin(double &v, unsigned long long zero)
+{
+#ifdef PLB_EMU_RUNTIME
+    (void)zero;
+#else
+    v = __longlong_as_double(__double_as_longlong(v) ^ (long long)zero);
+#endif
+}
+template <int COLL, int FORCING>
+__device__ __forceinline__ void pin_collision_constants(KParams &kp)
+{
+#if PLB_FUSED_PIN
+    const unsigned long long z = opaque_zero();
+    if constexpr (COLL == 2) {
+        pin(kp.mrt.k2, z); pin(kp.mrt.k4, z); pin(kp.mrt.k7, z); pin(kp.mrt.k8, z);
+        pin(kp.mrt.qa, z); pin(kp.mrt.qb, z);
+        pin(kp.w[0], z); pin(kp.w[1], z); pin(kp.w[5], z);
+        pin(kp.inv_cs_2, z); pin(kp.eps, z);
+        if constexpr (FORCING != 0) { pin(kp.mrt.hgx, z); pin(kp.mrt.hgy, z); }
+#if PLB_FUSED_PIN >= 2
+        if constexpr (FORCING == 2) {
+            pin(kp.gx, z); pin(kp.gy, z);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { pin(kp.mrt.k4cg[j], z); pin(kp.mrt.k2cg[j], z); }
+        }
+#endif
+    } else if constexpr (COLL == 0) {
+        pin(kp.omega, z); pin(kp.inv_cs_2, z); pin(kp.inv_cs_4, z); pin(kp.eps, z);
+        pin(kp.w[0], z); pin(kp.w[1], z); pin(kp.w[5], z);
+    }
+#else
+    (void)kp;
+#endif
+}
+
 // Stage 1 of one row: collide the pair (y, y + 1) and hand every
 // post-collision population to the lane that pulls it in the next step:
 // sa[k] is what node y receives in slot k, sb[k] what node y + 1 receives.
 // (For c_y = +1 lane 0's sa and for c_y = -1 lane 31's sb come from outside
 // the warp and are meaningless: those two nodes are not delivered.)
 template <int COLL, int FORCING>
-__device__ __forceinline__ void fused_stage1(const StepArgs &a, const double fa[Q],
+__device__ __forceinline__ void fused_stage1(const KParams &kp, const double fa[Q],
                                              const double fb[Q], double sa[Q],
                                              double sb[Q])
 {
     double ga[Q], gb[Q];
-    collide<COLL, FORCING>(a.p, fa, ga);
-    collide<COLL, FORCING>(a.p, fb, gb);
+    collide<COLL, FORCING>(kp, fa, ga);
+    collide<COLL, FORCING>(kp, fb, gb);
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
         if (d_cy[k] == 0) {
@@ -547,11 +683,13 @@ template <int COLL, int FORCING, int DEPTH>
 __global__ void __launch_bounds__(PLB_FUSED_BLOCK, fused_min_blocks(COLL, DEPTH))
 k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
              int64_t x_end, int32_t strips, int32_t rows_per_chunk,
-             unsigned *work_counter)
+             unsigned *work_counter, const PLB_GRID_CONSTANT TensorMap tmap)
 {
     constexpr int LEVELS = DEPTH - 1;              // hand-overs in registers
     const Layout &L = a.p.L;
     const int lane = threadIdx.x & 31;
+    KParams kp = a.p;
+    pin_collision_constants<COLL, FORCING>(kp);
 #if PLB_FUSED_DYN_SMEM
 #ifdef PLB_EMU_RUNTIME
     static __align__(128) unsigned char fused_smem[fused_smem_bytes(DEPTH)];
@@ -590,6 +728,18 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
     }
     __syncwarp();
     unsigned filled = 0;
+    // this lane's 16 bytes of population k in ring slot `slot`
+#if PLB_FUSED_TENSOR
+    // a warp's slot is one dense box: [slot][warp][k][lane]
+    auto ring_row = [&](int slot, int k) -> double2 * {
+        return reinterpret_cast<double2 *>(fused_smem) +
+               ((slot * (PLB_FUSED_BLOCK / 32) + wid) * Q + k) * 32 + lane;
+    };
+#else
+    auto ring_row = [&](int slot, int k) -> double2 * {
+        return &ring[slot][k][threadIdx.x];
+    };
+#endif
 #endif
     // One work item = one chunk of rows of one strip.  Statically a warp takes
     // the item of its own number; with a work counter (PLB_FUSED_DYNAMIC=1,
@@ -615,6 +765,17 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         // this lane still delivers node y / node y + 1 if ...
         const bool lane_a = 2 * lane >= LEVELS && 2 * lane <= 63 - LEVELS;
         const bool lane_b = 2 * lane + 1 >= LEVELS && 2 * lane + 1 <= 63 - LEVELS;
+        // which halves of the pair [y, y + 1] this lane stores, per c_y of the
+        // population (bit 0: the low half, bit 1: the high half): c_y = 0 own
+        // nodes, c_y = +1 (left neighbour's b, own a), c_y = -1 (own b, right
+        // neighbour's a)
+        const unsigned mode_0 = unsigned(lane_a) | unsigned(lane_b) << 1;
+        const unsigned mode_p =
+            unsigned(lane > 0 && 2 * lane - 1 <= 63 - LEVELS && 2 * lane - 1 >= LEVELS) |
+            unsigned(lane_a) << 1;
+        const unsigned mode_m =
+            unsigned(lane_b) |
+            unsigned(lane < 31 && 2 * lane + 2 >= LEVELS && 2 * lane + 2 <= 63 - LEVELS) << 1;
 
         // Rows xs - LEVELS .. xe - 1 + LEVELS go through level 0 in order (row
         // number i = 0 ..); row number i leaves level l (0-based) as the complete
@@ -624,6 +785,27 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         const double *row0 = a.fin + L.at(xs - LEVELS, y);     // pair of row i = 0
 #if PLB_FUSED_BULK
         constexpr int AHEAD = PLB_FUSED_STAGES;
+#if PLB_FUSED_TENSOR
+        // the warp's box: 64 columns from the strip's first, row number j of the
+        // item; a strip always begins inside the padded row
+        const int box_col = int(L.y0 + y) - 2 * lane;
+        const int box_row0 = int(xs) - LEVELS + 1;
+        constexpr unsigned run_bytes = 512;
+        auto fill = [&](int j) {
+            // cross-proxy fence + warp barrier: see the linear variant below
+#if PLB_FUSED_BULK_FENCE
+            fence_proxy_async_smem();
+#endif
+            __syncwarp();
+            if (lane == 0 && j < n_rows) {
+                const unsigned g = filled + unsigned(j);
+                const int slot = int(g % PLB_FUSED_STAGES);
+                unsigned long long *bar = &ring_bar[slot][wid];
+                mbar_expect_tx(bar, Q * run_bytes);
+                tensor_g2s(ring_row(slot, 0) - lane, &tmap, box_col, box_row0 + j, bar);
+            }
+        };
+#else
         // bytes of the warp's run that lie inside the padded row (the lanes
         // with in_row are a prefix of the warp), and the elected lane's view
         // of the run
@@ -647,10 +829,11 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
                 mbar_expect_tx(bar, Q * run_bytes);
 #pragma unroll
                 for (int k = 0; k < Q; ++k)
-                    bulk_g2s(&ring[g % PLB_FUSED_STAGES][k][wid * 32],
+                    bulk_g2s(ring_row(int(g % PLB_FUSED_STAGES), k) - lane,
                              run0 + k * plane + int64_t(j) * pitch, run_bytes, bar);
             }
         };
+#endif
 #pragma unroll
         for (int i = 0; i < AHEAD; ++i) fill(i);
 #elif PLB_FUSED_STAGES >= 2
@@ -679,11 +862,13 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         // deep flags of the row that is pushed in the NEXT iteration: fetched one
         // iteration ahead, so that the vote below never waits for them
         uint16_t dd_next = 0;
-        for (int i = 0; i < n_rows; ++i) {
+        // node index of this lane's pair in the row pushed in iteration i
+        // (x = xs + i - 2 LEVELS), advanced by one row per iteration
+        int64_t idx = L.at(xs - 2 * LEVELS, y);
+        for (int i = 0; i < n_rows; ++i, idx += pitch) {
             const uint16_t dd = dd_next;
             if (in_row && i + 1 >= 2 * LEVELS && i + 1 < n_rows)
-                dd_next = *reinterpret_cast<const uint16_t *>(
-                    deep + L.at(xs + i + 1 - 2 * LEVELS, y));
+                dd_next = *reinterpret_cast<const uint16_t *>(deep + idx + pitch);
             double fa[Q], fb[Q];
 #if PLB_FUSED_BULK
             {
@@ -693,8 +878,13 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
                     mbar_wait(&ring_bar[slot][wid], (g / PLB_FUSED_STAGES) & 1u);
 #pragma unroll
                 for (int k = 0; k < Q; ++k) {
+#if PLB_FUSED_TENSOR
+                    // columns outside the padded row were zero-filled by the unit
+                    const double2 v = *ring_row(slot, k);
+#else
                     double2 v = make_double2(0.0, 0.0);
-                    if (in_row) v = ring[slot][k][threadIdx.x];
+                    if (in_row) v = *ring_row(slot, k);
+#endif
                     fa[k] = v.x;
                     fb[k] = v.y;
                 }
@@ -737,7 +927,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
             for (int l = 0; l < LEVELS; ++l) {
                 if (!complete) break;
                 double sa[Q], sb[Q];
-                fused_stage1<COLL, FORCING>(a, fa, fb, sa, sb);
+                fused_stage1<COLL, FORCING>(kp, fa, fb, sa, sb);
 #if PLB_FUSED_BULK && PLB_FUSED_BULK_LATE
                 // refill only after the row has been collided: its values have
                 // then provably left shared memory (data dependence)
@@ -786,43 +976,32 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
             }
             if (!complete) continue;
 
-            const int64_t idx = L.at(xs + i - 2 * LEVELS, y);
             const bool da = (dd & 0xff) >= LEVELS && lane_a;
             const bool db = (dd >> 8) >= LEVELS && lane_b;
             if (!__any_sync(0xffffffffu, da || db)) continue;
 
             double ha[Q], hb[Q];
-            collide<COLL, FORCING>(a.p, fa, ha);
-            collide<COLL, FORCING>(a.p, fb, hb);
+            collide<COLL, FORCING>(kp, fa, ha);
+            collide<COLL, FORCING>(kp, fb, hb);
 
             if (__all_sync(0xffffffffu, (da || !lane_a) && (db || !lane_b))) {
                 // every node the warp can deliver is deep: 128-bit stores, pairs
                 // re-aligned by shuffle (a pair whose other half belongs to a lost
-                // node shrinks to a 64-bit store)
+                // node shrinks to a 64-bit store) -- three predicated stores per
+                // population, no divergent branch (st_pair)
+                char *row = reinterpret_cast<char *>(a.fout + idx);
 #pragma unroll
                 for (int k = 0; k < Q; ++k) {
-                    double *dst = a.fout + k * plane + idx + d_cx[k] * pitch;
-                    double lo, hi;
-                    bool lo_ok, hi_ok;
+                    double *dst = reinterpret_cast<double *>(row + a.push_off[k]);
                     if (d_cy[k] == 0) {
-                        lo = ha[k]; hi = hb[k];
-                        lo_ok = lane_a; hi_ok = lane_b;
+                        st_pair(dst, ha[k], hb[k], mode_0);
                     } else if (d_cy[k] == 1) {
                         // values move to y + 1, y + 2: pair [y, y+1] = (left b, own a)
-                        lo = __shfl_up_sync(0xffffffffu, hb[k], 1);
-                        hi = ha[k];
-                        lo_ok = lane > 0 && 2 * lane - 1 <= 63 - LEVELS && 2 * lane - 1 >= LEVELS;
-                        hi_ok = lane_a;
+                        st_pair(dst, __shfl_up_sync(0xffffffffu, hb[k], 1), ha[k], mode_p);
                     } else {
                         // values move to y - 1, y: pair [y, y+1] = (own b, right a)
-                        lo = hb[k];
-                        hi = __shfl_down_sync(0xffffffffu, ha[k], 1);
-                        lo_ok = lane_b;
-                        hi_ok = lane < 31 && 2 * lane + 2 >= LEVELS && 2 * lane + 2 <= 63 - LEVELS;
+                        st_pair(dst, hb[k], __shfl_down_sync(0xffffffffu, ha[k], 1), mode_m);
                     }
-                    if (lo_ok && hi_ok) st2(dst, lo, hi);
-                    else if (lo_ok) st1(dst, lo);
-                    else if (hi_ok) st1(dst + 1, hi);
                 }
             } else {
                 // strip touches a node that is not deep (domain edge, obstacle, ring)
@@ -1260,7 +1439,7 @@ int fused_strips(const Layout &L, int depth)
 template <int C, int F, int D>
 static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
                       int64_t x_end, int32_t rows_per_chunk, unsigned *work_counter,
-                      cudaStream_t st)
+                      const TensorMap &tmap, cudaStream_t st)
 {
     const int32_t strips = fused_strips(a.p.L, D);
     const int64_t chunks = (x_end - x_begin + rows_per_chunk - 1) / rows_per_chunk;
@@ -1301,14 +1480,15 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
     }
     PLB_LAUNCH_SMEM(COOP, (k_bulk_fused<C, F, D>), unsigned((warps + wpb - 1) / wpb),
                     PLB_FUSED_BLOCK, dyn_smem, st, a, deep, x_begin, x_end, strips,
-                    rows_per_chunk, work_counter);
+                    rows_per_chunk, work_counter, tmap);
 }
 
 const char *kernel_build_info()
 {
     static char text[320];
     if (!text[0]) {
-        const char *ring = PLB_FUSED_BULK         ? "tma-bulk"
+        const char *ring = PLB_FUSED_TENSOR       ? "tma-tensor"
+                           : PLB_FUSED_BULK       ? "tma-bulk"
                            : PLB_FUSED_STAGES < 2 ? "none"
                                                   : "cp.async";
         snprintf(text, sizeof text,
@@ -1330,19 +1510,85 @@ const char *kernel_build_info()
     return text;
 }
 
+bool fused_needs_tensor_map() { return PLB_FUSED_TENSOR != 0; }
+
+int make_lattice_tensor_map(TensorMap *out, const double *lattice, const Layout &L,
+                            char *why, size_t why_len)
+{
+    memset(out, 0, sizeof *out);
+#ifdef PLB_EMU_RUNTIME
+    // the emulated copy (tensor_g2s) reads the lattice through these four words
+    out->opaque[0] = reinterpret_cast<unsigned long long>(lattice);
+    out->opaque[1] = (unsigned long long)L.pitch;
+    out->opaque[2] = (unsigned long long)(L.nx + 2);
+    out->opaque[3] = (unsigned long long)L.plane;
+    (void)why;
+    (void)why_len;
+    return 0;
+#else
+    static_assert(sizeof(TensorMap) == sizeof(CUtensorMap), "CUtensorMap is 128 bytes");
+    typedef CUresult (*Encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                               const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                               const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    // the driver entry point through the runtime: libplb does not link libcuda
+    static Encode encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult found;
+        const cudaError_t rc = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn,
+                                                       cudaEnableDefault, &found);
+        if (rc != cudaSuccess || found != cudaDriverEntryPointSuccess || !fn) {
+            snprintf(why, why_len, "cuTensorMapEncodeTiled is not available (%s)",
+                     cudaGetErrorString(rc));
+            return rc != cudaSuccess ? int(rc) : -1;
+        }
+        encode = reinterpret_cast<Encode>(fn);
+    }
+    const cuuint64_t dims[3] = {cuuint64_t(L.pitch), cuuint64_t(L.nx + 2), cuuint64_t(Q)};
+    const cuuint64_t strides[2] = {cuuint64_t(L.pitch) * sizeof(double),
+                                   cuuint64_t(L.plane) * sizeof(double)};
+    const cuuint32_t box[3] = {64, 1, cuuint32_t(Q)};
+    const cuuint32_t elem[3] = {1, 1, 1};
+    int promo = 2;      // 128-byte L2 sectors promoted to 256 bytes: rows are 512 B runs
+    if (const char *v = getenv("PLB_TMA_L2_PROMOTION")) promo = atoi(v);
+    const CUresult rc = encode(
+        reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+        const_cast<double *>(lattice), dims, strides, box, elem,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+        promo == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+        : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+        : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                     : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        snprintf(why, why_len,
+                 "cuTensorMapEncodeTiled failed with CUresult %d (pitch %lld, rows %lld, "
+                 "plane %lld doubles)", int(rc), (long long)L.pitch, (long long)(L.nx + 2),
+                 (long long)L.plane);
+        return int(rc);
+    }
+    return 0;
+#endif
+}
+
 int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
                       int64_t x_begin, int64_t x_end, int32_t rows_per_chunk,
-                      unsigned *work_counter, cudaStream_t stream)
+                      unsigned *work_counter, const TensorMap *tmap_ptr,
+                      cudaStream_t stream)
 {
     if (x_end <= x_begin || depth < 2 || depth > 3) return 0;
+    static const TensorMap no_map = {};
+    if (PLB_FUSED_TENSOR && !tmap_ptr) return 0;
+    const TensorMap &tmap = tmap_ptr ? *tmap_ptr : no_map;
 #define PLB_CASE(C, F)                                                        \
     if (a.collision == C && a.forcing == F) {                                 \
         if (depth == 2)                                                       \
             run_fused<C, F, 2>(a, deep, x_begin, x_end, rows_per_chunk,       \
-                               work_counter, stream);                         \
+                               work_counter, tmap, stream);                   \
         else                                                                  \
             run_fused<C, F, 3>(a, deep, x_begin, x_end, rows_per_chunk,       \
-                               work_counter, stream);                         \
+                               work_counter, tmap, stream);                   \
         return 1;                                                             \
     }
     PLB_CASE(0, 0) PLB_CASE(0, 1) PLB_CASE(0, 2)

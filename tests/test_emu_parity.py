@@ -345,14 +345,19 @@ def test_residues_and_link_record_with_pairing(emu):
 VARIANT_FLAGS = {
     # PLB_FUSED_BULK=1: the prefetch ring filled by TMA bulk copies that
     # complete on per-warp mbarriers (three slots)
-    "bulk_s3": ["-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=3"],
+    "bulk_s3": ["-DPLB_FUSED_CARRY_SMEM=0", "-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=3",
+                "-DPLB_FUSED_TENSOR=0"],
     # ... and PLB_FUSED_CARRY_SMEM=1: the carried populations in shared memory
     # (everything in dynamic shared memory)
     "carry_bulk_s3": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1",
-                      "-DPLB_FUSED_STAGES=3"],
+                      "-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_TENSOR=0"],
     # ... with a ring of one slot, refilled as soon as it has been read
     "carry_bulk_s1": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1",
-                      "-DPLB_FUSED_STAGES=1"],
+                      "-DPLB_FUSED_STAGES=1", "-DPLB_FUSED_TENSOR=0"],
+    # PLB_FUSED_TENSOR=1 (the shipped default with one slot): a warp's row is one
+    # rank-3 tensor copy into a dense per-warp slot; here with three slots
+    "tensor_s3": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1",
+                  "-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_TENSOR=1"],
 }
 
 

@@ -46,6 +46,18 @@ VARIANTS = {
     "cb_s1_mb4_late": fused(1, 1, 1, 4, 3, extra=["-DPLB_FUSED_BULK_LATE=1"]),
     "cb_s1_mb4_d3mb2": fused(1, 1, 1, 4, 2),
     "carry_bulk_mb4": fused(1, 1, 2, 4, 3),
+    # round 2, second half: the ring filled by ONE rank-3 tensor copy per row
+    # (PLB_FUSED_TENSOR), collision constants pinned in registers
+    # (PLB_FUSED_PIN), four CTAs of 128 registers at depth 3 -- the shipped
+    # default is t1_p1; each variant switches one thing
+    "t1_p1": fused(1, 1, 1, 4, 4, extra=["-DPLB_FUSED_TENSOR=1", "-DPLB_FUSED_PIN=1"]),
+    "t0_p1": fused(1, 1, 1, 4, 4, extra=["-DPLB_FUSED_TENSOR=0", "-DPLB_FUSED_PIN=1"]),
+    "t1_p0": fused(1, 1, 1, 4, 4, extra=["-DPLB_FUSED_TENSOR=1", "-DPLB_FUSED_PIN=0"]),
+    "t1_p2": fused(1, 1, 1, 4, 4, extra=["-DPLB_FUSED_TENSOR=1", "-DPLB_FUSED_PIN=2"]),
+    "t1_p1_d3mb3": fused(1, 1, 1, 4, 3, extra=["-DPLB_FUSED_TENSOR=1", "-DPLB_FUSED_PIN=1"]),
+    "t1_p1_s2": fused(1, 1, 2, 4, 3, extra=["-DPLB_FUSED_TENSOR=1", "-DPLB_FUSED_PIN=1"]),
+    "t1_p1_late": fused(1, 1, 1, 4, 4, extra=["-DPLB_FUSED_TENSOR=1", "-DPLB_FUSED_PIN=1",
+                                              "-DPLB_FUSED_BULK_LATE=1"]),
 }
 
 if __name__ == "__main__":
