@@ -574,12 +574,17 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device,
               "k_bulk_fused<depth 2>" if pairs else
               "k_bulk_vec2" if info["variant"] else "k_bulk_scalar")
     traffic_key = workload + ("_fused3" if triples else "_fused" if pairs else "")
+    alg_per_launch = ALGORITHMIC_BYTES_PER_NODE * dram_nodes / max(1, bulk_n)
+    traffic = ncu_traffic(traffic_key)
+    if traffic is not None and not 0.9 <= traffic / alg_per_launch <= 1.3:
+        # the committed capture is of another slab size (a strong-scaling
+        # slab at N > 1): it says nothing about this launch
+        traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(traffic_key),
+                "traffic": traffic,
                 "kernel": kernel,
-                "algorithmic_bytes_per_launch":
-                    ALGORITHMIC_BYTES_PER_NODE * dram_nodes / max(1, bulk_n),
+                "algorithmic_bytes_per_launch": alg_per_launch,
                 "steps_per_launch": 3 if triples else 2 if pairs else 1,
                 "bytes_per_node_and_step":
                     ALGORITHMIC_BYTES_PER_NODE * dram_nodes / max(1, node_steps),

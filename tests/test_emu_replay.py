@@ -36,3 +36,21 @@ def test_solver_life_cycle_on_the_emulator(depth, guard, select):
         capture_output=True, text=True, timeout=1500, env=env, cwd=os.path.dirname(HERE))
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-2000:]
     assert " passed" in proc.stdout
+
+
+def test_smoke_entry_point_on_the_emulator():
+    """__graft_entry__.smoke() -- what the driver runs on cuda:0 before the
+    bench -- replayed against the emulated library: its own bookkeeping (how
+    many of its steps the several-steps-per-pass kernel took) must agree with
+    the shipped defaults."""
+    lib = build_emu.build()
+    env = dict(os.environ, PLB_LIB=lib, PLB_EMU_TESTING="1")
+    env.pop("PLB_FUSE", None)
+    env.pop("PLB_FUSE_DEPTH", None)
+    proc = subprocess.run(
+        [sys.executable, "-c",
+         "from pylabolt_b200 import capi; capi._accept_emulated_build = True; "
+         "import __graft_entry__ as g; g.smoke()"],
+        capture_output=True, text=True, timeout=900, env=env, cwd=os.path.dirname(HERE))
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-3000:]
+    assert "three-step" in proc.stdout
