@@ -50,9 +50,15 @@ struct Moments {
 // DFMA, an error of an ulp, and none of the range checks and the slow-path
 // call an IEEE division carries (x = rho + eps is of order one).  The BGK
 // paths, which are pinned to the reference bit for bit, keep the division.
+#ifndef PLB_MRT_RCP_NEWTON
+#define PLB_MRT_RCP_NEWTON 1
+#endif
+#ifndef PLB_MRT_PAIR_FMA3
+#define PLB_MRT_PAIR_FMA3 1
+#endif
 __device__ __forceinline__ double rcp_newton(double x)
 {
-#ifdef PLB_EMU_RUNTIME
+#if defined(PLB_EMU_RUNTIME) || !PLB_MRT_RCP_NEWTON
     return 1.0 / x;
 #else
     double r;
@@ -310,10 +316,15 @@ __device__ __forceinline__ void stress_pair(const KParams &p, double ux,
     }
     if constexpr (FORCING != 0) odd = p.inv_cs_2 * cu + p.mrt.k2cg[slot];
     else odd = p.inv_cs_2 * cu;
+#if PLB_MRT_PAIR_FMA3
     // wrho (even +- odd) + proj as three fused multiply-adds
     const double centre = fma(wrho, even, proj);
     g[K] = fma(wrho, odd, centre);
     g[KI] = fma(-wrho, odd, centre);
+#else
+    g[K] = wrho * (even + odd) + proj;
+    g[KI] = wrho * (even - odd) + proj;
+#endif
 }
 
 template <int FORCING>

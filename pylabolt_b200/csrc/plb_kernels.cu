@@ -442,11 +442,19 @@ __host__ __device__ constexpr int fused_smem_bytes(int depth)
 #ifndef PLB_FUSED_MINBLOCKS_D3
 #define PLB_FUSED_MINBLOCKS_D3 (512 / PLB_FUSED_BLOCK)
 #endif
+#ifndef PLB_FUSED_MINBLOCKS_D3_MRT
+#define PLB_FUSED_MINBLOCKS_D3_MRT (384 / PLB_FUSED_BLOCK)
+#endif
 __host__ __device__ constexpr int fused_min_blocks(int coll, int depth)
 {
     // three steps per pass: shared memory (55 KB per CTA) admits four CTAs of
     // 128 threads per SM, i.e. 128 registers per thread
-    if (depth >= 3) return PLB_FUSED_MINBLOCKS_D3;
+    // Measured (profiles/r02_fused_sweep_v5_tensor.txt): the two-stress-moment
+    // MRT kernel is faster with three CTAs of 142 registers (117.3 GLUPS) than
+    // with four of 119 (114.5); the reference-ordered BGK kernels the other
+    // way round (109.1 with three of 134, 113.7 with four of 128); the
+    // nine-rate MRT spills beyond 128.
+    if (depth >= 3) return coll == 2 ? PLB_FUSED_MINBLOCKS_D3_MRT : PLB_FUSED_MINBLOCKS_D3;
 #ifdef PLB_FUSED_MINBLOCKS_BGK
     return coll == 0 ? PLB_FUSED_MINBLOCKS_BGK : PLB_FUSED_MINBLOCKS;
 #else

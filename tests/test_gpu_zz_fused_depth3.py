@@ -48,7 +48,7 @@ def test_default_is_three_steps_per_pass(monkeypatch):
         info = s.plb.fused_info()
         assert info["triples"] == 6 and info["pairs"] == 1
         got = s.fields_to_host()
-        assert "ring=tma-bulk carry=shared" in s.plb.build_info()
+        assert "ring=tma-tensor carry=shared" in s.plb.build_info()
     finally:
         s.close()
     want, _ = _fields(factory, 21, "0", True, monkeypatch)

@@ -58,6 +58,15 @@ VARIANTS = {
     "t1_p1_s2": fused(1, 1, 2, 4, 3, extra=["-DPLB_FUSED_TENSOR=1", "-DPLB_FUSED_PIN=1"]),
     "t1_p1_late": fused(1, 1, 1, 4, 4, extra=["-DPLB_FUSED_TENSOR=1", "-DPLB_FUSED_PIN=1",
                                               "-DPLB_FUSED_BULK_LATE=1"]),
+    # accuracy of the MRT shortcuts against the oracle over hundreds of steps
+    # (bench.py's in-run parity): IEEE division instead of the Newton
+    # reciprocal, the two-add pair instead of the three-FMA pair
+    "mrt_div": ["-DPLB_MRT_RCP_NEWTON=0"],
+    "mrt_pair_old": ["-DPLB_MRT_PAIR_FMA3=0"],
+    "mrt_div_pair_old": ["-DPLB_MRT_RCP_NEWTON=0", "-DPLB_MRT_PAIR_FMA3=0"],
+    # two ring slots with the per-model CTA counts of the default
+    "s2": ["-DPLB_FUSED_STAGES=2"],
+    "s2_mrt4": ["-DPLB_FUSED_STAGES=2", "-DPLB_FUSED_MINBLOCKS_D3_MRT=4"],
 }
 
 if __name__ == "__main__":
