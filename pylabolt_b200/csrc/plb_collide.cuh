@@ -53,8 +53,13 @@ struct Moments {
 #ifndef PLB_MRT_RCP_NEWTON
 #define PLB_MRT_RCP_NEWTON 1
 #endif
+// PLB_MRT_PAIR_FMA3=1 forms a direction pair with three FMAs instead of two
+// adds and two FMAs (one fp64 instruction less per pair, +1 % GLUPS) -- and
+// doubles the distance to the oracle on the channel benchmark (1.62e-12
+// against 7.2e-13 relative after 400 steps, bench.py's in-run parity on the
+// B200): off.  The Newton reciprocal changes that distance in no digit.
 #ifndef PLB_MRT_PAIR_FMA3
-#define PLB_MRT_PAIR_FMA3 1
+#define PLB_MRT_PAIR_FMA3 0
 #endif
 __device__ __forceinline__ double rcp_newton(double x)
 {
