@@ -490,7 +490,7 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device,
     comm.Barrier()
     plb.kernel_launches(reset=True)
     plb.profile_enable(True)
-    groups_before = (plb.fused_info()["pairs"], plb.fused_info()["triples"])
+    groups_before = tuple(plb.fused_info()[k] for k in ("pairs", "triples", "quads"))
     repeat_ms = []
     launches = 0
     sampler.mark_start()
@@ -561,19 +561,22 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device,
     finfo = plb.fused_info()
     pairs = finfo["pairs"] - groups_before[0]
     triples = finfo["triples"] - groups_before[1]
-    singles = steps_timed - 2 * pairs - 3 * triples
+    quads = finfo["quads"] - groups_before[2]
+    singles = steps_timed - 2 * pairs - 3 * triples - 4 * quads
     bulk_ms_per_step = bulk_ms / steps_timed
     node_steps = (2 * finfo["n_deep"] * pairs + 3 * finfo["n_deep3"] * triples +
-                  info["n_bulk_timed"] * singles)
+                  4 * finfo["n_deep4"] * quads + info["n_bulk_timed"] * singles)
     dram_nodes = (finfo["n_deep"] * pairs + finfo["n_deep3"] * triples +
-                  info["n_bulk_timed"] * singles)
+                  finfo["n_deep4"] * quads + info["n_bulk_timed"] * singles)
     achieved = ALGORITHMIC_BYTES_PER_NODE * dram_nodes / (bulk_ms * 1e-3) / 1e9
     step_equiv = ALGORITHMIC_BYTES_PER_NODE * node_steps / (bulk_ms * 1e-3) / 1e9
-    fused = pairs + triples > 0
-    kernel = ("k_bulk_fused<depth 3>" if triples else
+    fused = pairs + triples + quads > 0
+    kernel = ("k_bulk_fused<depth 4>" if quads else
+              "k_bulk_fused<depth 3>" if triples else
               "k_bulk_fused<depth 2>" if pairs else
               "k_bulk_vec2" if info["variant"] else "k_bulk_scalar")
-    traffic_key = workload + ("_fused3" if triples else "_fused" if pairs else "")
+    traffic_key = workload + ("_fused4" if quads else "_fused3" if triples else
+                              "_fused" if pairs else "")
     alg_per_launch = ALGORITHMIC_BYTES_PER_NODE * dram_nodes / max(1, bulk_n)
     traffic = ncu_traffic(traffic_key)
     if traffic is not None and not 0.9 <= traffic / alg_per_launch <= 1.3:
@@ -585,14 +588,15 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device,
                 "traffic": traffic,
                 "kernel": kernel,
                 "algorithmic_bytes_per_launch": alg_per_launch,
-                "steps_per_launch": 3 if triples else 2 if pairs else 1,
+                "steps_per_launch": 4 if quads else 3 if triples else 2 if pairs else 1,
                 "bytes_per_node_and_step":
                     ALGORITHMIC_BYTES_PER_NODE * dram_nodes / max(1, node_steps),
                 "step_equivalent_gbs": step_equiv,
                 "step_equivalent_frac": step_equiv / peak,
-                "fused": {k: finfo[k] for k in ("active", "n_deep", "n_deep3",
+                "fused": {k: finfo[k] for k in ("active", "n_deep", "n_deep3", "n_deep4",
                                                 "n_list1", "rows", "strips")},
-                "pairs": pairs, "triples": triples, "single_steps": singles,
+                "pairs": pairs, "triples": triples, "quads": quads,
+                "single_steps": singles,
                 "face_transport": ["none", "own ghost rows", "nccl",
                                    "p2p stores"][info["faces"]],
                 "launches_per_step": bulk_n / steps_timed,

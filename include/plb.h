@@ -165,13 +165,15 @@ int plb_sync(plb_handle h);
  * the rest arrives; every other entry point first completes what was held
  * back.  Environment: PLB_FUSE=0 disables the path, PLB_FUSE=2 uses it on any
  * lattice that has such nodes (default: lattices where they dominate);
- * PLB_FUSE_DEPTH=3 groups three steps (48 B per node and step; nodes whose
- * neighbourhood of radius two is plain fluid; opt-in).
+ * PLB_FUSE_DEPTH=2 / 3 / 4 sets the steps per pass (default: per collision
+ * model, from measurement; 48 / 36 B per node and step at 3 / 4; a depth-d
+ * pass advances the nodes whose neighbourhood of radius d - 1 is plain fluid).
  * out = {steps per pass in use (0: off), nodes advanced by the two-step kernel,
  *        by the three-step kernel, nodes of the first list pass,
  *        two-step passes executed, rows per warp chunk, y strips,
- *        three-step passes executed} */
-int plb_fused_info(plb_handle h, int64_t out[8]);
+ *        three-step passes executed, nodes advanced by the four-step kernel,
+ *        four-step passes executed} */
+int plb_fused_info(plb_handle h, int64_t out[10]);
 
 /* Device memory held by the handle, in bytes (the reference keeps its
  * `*_device` mirrors for the process lifetime, base/fields.py:192-227):

@@ -359,12 +359,12 @@ class Plb:
         return dict(zip(keys, out[:8]))
 
     def fused_info(self):
-        """State of the two-steps-per-pass path (plb_fused_info)."""
-        out = (ctypes.c_int64 * 8)()
+        """State of the several-steps-per-pass path (plb_fused_info)."""
+        out = (ctypes.c_int64 * 10)()
         self._check(self.lib.plb_fused_info(self._h, out))
         keys = ("active", "n_deep", "n_deep3", "n_list1", "pairs", "rows",
-                "strips", "triples")
-        return dict(zip(keys, out[:8]))
+                "strips", "triples", "n_deep4", "quads")
+        return dict(zip(keys, out[:10]))
 
     def memory_info(self):
         """Device bytes held by this handle (plb_memory_info)."""

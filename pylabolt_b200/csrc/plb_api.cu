@@ -167,28 +167,30 @@ struct plb_solver {
 
     // Several steps per pass (step_fused): PLB_FUSE = 0 off, 1 when the
     // geometry qualifies (default), 2 whenever there is a deep node at all;
-    // PLB_FUSE_DEPTH = steps per pass (3 by default since round 2; 2).
+    // PLB_FUSE_DEPTH = steps per pass, 2 .. MAX_FUSE_DEPTH (default per
+    // collision model, see plb_create).
     int fuse_mode = PLB_FUSE_DEFAULT;
     int fuse_depth = 3;
+    bool fuse_depth_from_env = false;
     int fused_depth_ok = 0;              // largest depth the geometry qualifies for (0: none)
-    double *f_mid[2] = {nullptr, nullptr};   // compact scratch lattices (lazy)
+    double *f_mid[MAX_FUSE_DEPTH - 1] = {};   // compact scratch lattices (lazy)
     // node index -> compact scratch lattice, one entry per 16 nodes (lat_off);
     // entry 0 is a spare segment that absorbs anything unlisted
     int32_t *mid_map_dev = nullptr;
     std::vector<int32_t> mid_map_host;
     int64_t mid_plane = 0;               // doubles per population of a scratch lattice
-    uint8_t *deep_dev = nullptr;         // distance to the nearest non-bulk node - 1, capped at 2
+    uint8_t *deep_dev = nullptr;         // distance to the nearest non-bulk node - 1, capped at fuse_depth - 1
     // list p (0-based) = nodes of list pass p + 1 of a depth-d group,
     // lists[d - 2][p]; the last one holds the fluid nodes that are not deep enough
-    LinkNode *lists_dev[2][3] = {};
-    int64_t n_lists[2][3] = {};
-    int64_t n_deep[2] = {0, 0};          // nodes the depth-2 / depth-3 kernel advances
-    // rows a warp marches over per work item, for two / three steps per pass
-    // (PLB_FUSED_ROWS sets both)
-    int32_t fused_rows[2] = {32, 64};
+    LinkNode *lists_dev[MAX_FUSE_DEPTH - 1][MAX_FUSE_DEPTH] = {};
+    int64_t n_lists[MAX_FUSE_DEPTH - 1][MAX_FUSE_DEPTH] = {};
+    int64_t n_deep[MAX_FUSE_DEPTH - 1] = {};   // nodes the depth-2 / -3 / -4 kernel advances
+    // rows a warp marches over per work item, for two / three / four steps per
+    // pass (PLB_FUSED_ROWS sets all)
+    int32_t fused_rows[MAX_FUSE_DEPTH - 1] = {32, 64, 64};
     unsigned *work_counter = nullptr;    // PLB_FUSED_DYNAMIC=1: persistent grid, work queue
     int64_t pending = 0;                 // plain steps held back for grouping
-    int64_t groups_done[2] = {0, 0};
+    int64_t groups_done[MAX_FUSE_DEPTH - 1] = {};
 
     int64_t launches = 0;
     int64_t steps_done = 0;
@@ -433,7 +435,7 @@ StepArgs step_args(const plb_solver *s, const double *fin, double *fout)
             a.push_off[k] = (int64_t(k) * s->L.plane + cx[k] * s->L.pitch) *
                             int64_t(sizeof(double));
     }
-    for (int m = 0; m < 2; ++m) {
+    for (int m = 0; m < MAX_FUSE_DEPTH - 1; ++m) {
         if (!s->f_mid[m]) continue;
         if (fin == s->f_mid[m]) {
             a.fin_map = s->mid_map_dev;
@@ -615,7 +617,7 @@ int step_fused(plb_solver *s, int depth)
             cudaGetLastError();
             s->f_mid[m] = nullptr;
             // no room for the scratch lattice: fall back to what fits
-            s->fused_depth_ok = m == 0 ? 0 : 2;
+            s->fused_depth_ok = m == 0 ? 0 : m + 1;
             return PLB_ERR_NOMEM;
         }
         CUDA_TRY(cudaMemsetAsync(s->f_mid[m], 0, bytes, s->stream));
@@ -671,6 +673,18 @@ int step_fused(plb_solver *s, int depth)
     return PLB_OK;
 }
 
+// Steps per pass by default, per collision kernel (PLB_FUSE_DEPTH overrides).
+// Measured on the B200 (profiles/): the reference-ordered BGK kernels are
+// bound by the fp64 pipe at three steps per pass, a fourth only adds halo
+// work; the two-stress-moment MRT kernel is bound by HBM at three.
+#ifndef PLB_FUSE_DEPTH_MRT
+#define PLB_FUSE_DEPTH_MRT 3
+#endif
+int default_fuse_depth(int kernel_collision)
+{
+    return kernel_collision == 2 ? PLB_FUSE_DEPTH_MRT : 3;
+}
+
 // Steps per pass the solver groups plain steps into right now (1: none).
 int fused_depth(const plb_solver *s)
 {
@@ -689,7 +703,7 @@ int run_steps(plb_solver *s, int64_t n, int32_t flags)
     const int64_t plain = flags ? n - 1 : n;
     for (;;) {
         int d = fused_depth(s);
-        if (d > plain - i) d = (plain - i >= 2 && fused_depth(s) >= 2) ? 2 : 1;
+        if (d > plain - i) d = d >= 2 ? int(plain - i) : 1;   // a remainder as a smaller group
         if (d < 2) break;
         const int rc = step_fused(s, d);
         if (rc == PLB_ERR_NOMEM) continue;      // fused_depth() has shrunk
@@ -938,8 +952,15 @@ int plb_create(const plb_config *c, plb_handle *out)
         s->variant = (strcmp(v, "scalar") == 0) ? 0 : 1;
     if (const char *v = getenv("PLB_FUSE")) s->fuse_mode = atoi(v);
     if (s->fuse_mode < 0 || s->fuse_mode > 2) s->fuse_mode = PLB_FUSE_DEFAULT;
-    if (const char *v = getenv("PLB_FUSE_DEPTH")) s->fuse_depth = atoi(v);
-    if (s->fuse_depth < 2 || s->fuse_depth > 3) s->fuse_depth = 3;
+    s->fuse_depth_from_env = false;
+    if (const char *v = getenv("PLB_FUSE_DEPTH")) {
+        s->fuse_depth = atoi(v);
+        s->fuse_depth_from_env = true;
+    }
+    if (s->fuse_depth < 2 || s->fuse_depth > MAX_FUSE_DEPTH) {
+        s->fuse_depth = 3;
+        s->fuse_depth_from_env = false;
+    }
     s->kernel_collision = c->collision;
     if (c->collision == PLB_MRT) {
         // S = (1,..,1,s7,s8) as in base/collision_operator.py:159-163 needs
@@ -949,6 +970,7 @@ int plb_create(const plb_config *c, plb_handle *out)
         const char *g = getenv("PLB_MRT_GENERAL");
         if (reference_rates && !(g && g[0] == '1')) s->kernel_collision = 2;
     }
+    if (!s->fuse_depth_from_env) s->fuse_depth = default_fuse_depth(s->kernel_collision);
 
     auto cleanup = [&](int rc) {
         plb_destroy(s);
@@ -1006,12 +1028,12 @@ void plb_destroy(plb_handle s)
     close_p2p(s);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (int i = 0; i < 2; ++i) cudaFree(s->f[i]);
-    for (int m = 0; m < 2; ++m) cudaFree(s->f_mid[m]);
+    for (int m = 0; m < MAX_FUSE_DEPTH - 1; ++m) cudaFree(s->f_mid[m]);
     cudaFree(s->mid_map_dev);
     cudaFree(s->deep_dev);
     cudaFree(s->work_counter);
-    for (int d = 0; d < 2; ++d)
-        for (int p = 0; p < 3; ++p) cudaFree(s->lists_dev[d][p]);
+    for (int d = 0; d < MAX_FUSE_DEPTH - 1; ++d)
+        for (int p = 0; p < MAX_FUSE_DEPTH; ++p) cudaFree(s->lists_dev[d][p]);
     cudaFree(s->mom);
     cudaFree(s->mom_old);
     cudaFree(s->res_partials);
@@ -1268,19 +1290,45 @@ int plb_finalize_geometry(plb_handle s)
                 if (uniform) tmpl[k].assign(out, out + P);
             }
         }
+        // One more erosion per further step per pass: a node whose nine
+        // neighbours all carry the cap so far is one ring deeper.  In place,
+        // row by row: hq[r][i] = rows r's nodes i-1, i, i+1 all at the cap, made
+        // from the still unmodified row before row r - 1 is raised.
+        uint8_t cap = 2;
+        for (; cap < uint8_t(s->fuse_depth - 1); ++cap) {
+            const int64_t R = nx + 2;
+            std::vector<uint8_t> hq(size_t(3 * P), 0);
+            auto row = [&](int64_t r) { return hq.data() + (r % 3) * P; };
+            auto make = [&](int64_t r) {
+                const uint8_t *in = deep.data() + r * P;
+                uint8_t *o = row(r);
+                o[0] = o[P - 1] = 0;
+                for (int64_t i = 1; i + 1 < P; ++i)
+                    o[i] = uint8_t((in[i - 1] == cap) & (in[i] == cap) & (in[i + 1] == cap));
+            };
+            make(0);
+            make(1);
+            for (int64_t r = 1; r + 1 < R; ++r) {
+                make(r + 1);
+                const uint8_t *u = row(r - 1), *m = row(r), *d = row(r + 1);
+                uint8_t *out = deep.data() + r * P;
+                for (int64_t i = 0; i < P; ++i) out[i] = uint8_t(out[i] + (u[i] & m[i] & d[i]));
+            }
+        }
         lap("deep flags");
         // candidates: interior nodes that are not fully deep (a few rings)
         std::vector<int64_t> candidates;
+        const uint64_t all_cap = 0x0101010101010101ull * cap;
         for (int64_t x = 0; x < nx; ++x) {
             const uint8_t *d = deep.data() + L.at(x, 0);
             int64_t y = 0;
             while (y < ny) {
                 uint64_t w;
-                if (y + 8 <= ny && (memcpy(&w, d + y, 8), w == 0x0202020202020202ull)) {
+                if (y + 8 <= ny && (memcpy(&w, d + y, 8), w == all_cap)) {
                     y += 8;
                     continue;
                 }
-                if (d[y] != 2) candidates.push_back(L.at(x, y));
+                if (d[y] != cap) candidates.push_back(L.at(x, y));
                 ++y;
             }
         }
@@ -1385,7 +1433,7 @@ int plb_finalize_geometry(plb_handle s)
             CUDA_TRY(cudaMalloc(&s->deep_dev, deep.size()));
             CUDA_TRY(cudaMemcpy(s->deep_dev, deep.data(), deep.size(), cudaMemcpyHostToDevice));
             if (const char *v = getenv("PLB_FUSED_ROWS")) {
-                s->fused_rows[0] = s->fused_rows[1] = std::max(1, atoi(v));
+                s->fused_rows[0] = s->fused_rows[1] = s->fused_rows[2] = std::max(1, atoi(v));
             } else {
                 // Chunk height measured on B200 (profiles/): two steps per pass:
                 // 32 rows beat 64 / 128 / 512 although 2 of 34 row loads are
@@ -1396,6 +1444,7 @@ int plb_finalize_geometry(plb_handle s)
                 const int64_t want = nx * fused_strips(L, 2) / (148 * 16 * 4);
                 s->fused_rows[0] = int32_t(std::min<int64_t>(32, std::max<int64_t>(8, want)));
                 s->fused_rows[1] = int32_t(std::min<int64_t>(64, std::max<int64_t>(8, want)));
+                s->fused_rows[2] = int32_t(std::min<int64_t>(64, std::max<int64_t>(8, want)));
             }
         }
     }
@@ -1568,7 +1617,7 @@ int plb_step(plb_handle s, int64_t n_steps, int32_t flags)
     return PLB_OK;
 }
 
-int plb_fused_info(plb_handle s, int64_t out[8])
+int plb_fused_info(plb_handle s, int64_t out[10])
 {
     if (!s || !out) return fail(PLB_ERR_INVALID, "null argument");
     const int d = fused_depth(s);
@@ -1577,9 +1626,11 @@ int plb_fused_info(plb_handle s, int64_t out[8])
     out[2] = s->n_deep[1];
     out[3] = d >= 2 ? s->n_lists[d - 2][0] : 0;
     out[4] = s->groups_done[0];
-    out[5] = s->fused_rows[d >= 3 ? 1 : 0];
+    out[5] = s->fused_rows[d >= 2 ? d - 2 : 0];
     out[6] = fused_strips(s->L, d >= 2 ? d : 2);
     out[7] = s->groups_done[1];
+    out[8] = s->n_deep[2];
+    out[9] = s->groups_done[2];
     return PLB_OK;
 }
 
@@ -1591,12 +1642,13 @@ int plb_memory_info(plb_handle s, int64_t out[6])
     out[0] = 2 * Q * plane_bytes;
     out[1] = (s->mom ? 3 : 0) * plane_bytes + (s->mom_old ? 3 : 0) * plane_bytes;
     out[2] = 0;
-    for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < MAX_FUSE_DEPTH - 1; ++m)
         if (s->f_mid[m]) out[2] += Q * s->mid_plane * int64_t(sizeof(double));
     if (s->mid_map_dev) out[2] += int64_t(s->mid_map_host.size() * sizeof(int32_t));
     int64_t lists = s->n_links * int64_t(sizeof(LinkNode));
-    for (int d = 0; d < 2; ++d)
-        for (int p = 0; p < 3; ++p) lists += s->n_lists[d][p] * int64_t(sizeof(LinkNode));
+    for (int d = 0; d < MAX_FUSE_DEPTH - 1; ++d)
+        for (int p = 0; p < MAX_FUSE_DEPTH; ++p)
+            lists += s->n_lists[d][p] * int64_t(sizeof(LinkNode));
     out[3] = s->L.plane * (s->deep_dev ? 2 : 1) + lists + 2 * int64_t(s->staging_bytes) +
              (s->exch_dev ? s->n_links * 8 * int64_t(sizeof(double)) : 0);
     size_t free_b = 0, total_b = 0;

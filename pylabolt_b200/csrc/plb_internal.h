@@ -7,6 +7,8 @@
 namespace plb {
 
 constexpr int Q = 9;
+// most steps k_bulk_fused advances per pass (instantiated for 2 .. this)
+constexpr int MAX_FUSE_DEPTH = 4;
 
 // D2Q9 direction tables, pylabolt/base/lattice.py:50-60.
 #define PLB_CX_LIST {0, 1, 0, -1, 0, 1, -1, -1, 1}
@@ -166,10 +168,10 @@ bool fused_needs_tensor_map();
 // All return the number of kernels launched (0 if nothing to do).
 int launch_bulk(const StepArgs &a, int64_t x_begin, int64_t x_end, int variant,
                 cudaStream_t stream);
-// `depth` (2 or 3) steps in one pass over the nodes of columns [x_begin, x_end)
-// whose deep[] value is >= depth - 1 (fin = time t, fout = time t + depth);
-// deep[] is one byte per node: the Chebyshev distance up to which all
-// neighbours are bulk nodes, capped at 2.
+// `depth` (2 .. MAX_FUSE_DEPTH) steps in one pass over the nodes of columns
+// [x_begin, x_end) whose deep[] value is >= depth - 1 (fin = time t, fout =
+// time t + depth); deep[] is one byte per node: the Chebyshev distance up to
+// which all neighbours are bulk nodes, capped at the largest depth in use - 1.
 // work_counter: null = one work item per warp; else a device word (zeroed by
 // the launcher) from which the warps of a persistent grid draw their items.
 // tmap: the TMA descriptor of lattice a.fin (make_lattice_tensor_map), through

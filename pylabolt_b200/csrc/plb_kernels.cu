@@ -1585,7 +1585,7 @@ int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
                       unsigned *work_counter, const TensorMap *tmap_ptr,
                       cudaStream_t stream)
 {
-    if (x_end <= x_begin || depth < 2 || depth > 3) return 0;
+    if (x_end <= x_begin || depth < 2 || depth > 4) return 0;
     static const TensorMap no_map = {};
     if (PLB_FUSED_TENSOR && !tmap_ptr) return 0;
     const TensorMap &tmap = tmap_ptr ? *tmap_ptr : no_map;
@@ -1594,8 +1594,11 @@ int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
         if (depth == 2)                                                       \
             run_fused<C, F, 2>(a, deep, x_begin, x_end, rows_per_chunk,       \
                                work_counter, tmap, stream);                   \
-        else                                                                  \
+        else if (depth == 3)                                                  \
             run_fused<C, F, 3>(a, deep, x_begin, x_end, rows_per_chunk,       \
+                               work_counter, tmap, stream);                   \
+        else                                                                  \
+            run_fused<C, F, 4>(a, deep, x_begin, x_end, rows_per_chunk,       \
                                work_counter, tmap, stream);                   \
         return 1;                                                             \
     }

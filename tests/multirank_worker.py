@@ -74,8 +74,11 @@ def global_oracle(sim):
 
 
 def fuse_options(tokens):
-    """Spec suffixes -> (PLB_FUSE, PLB_FUSE_DEPTH): "fuse2" / "fuse3" force two /
-    three steps per pass on any lattice, "fuse0" single steps only."""
+    """Spec suffixes -> (PLB_FUSE, PLB_FUSE_DEPTH): "fuse2" / "fuse3" / "fuse4"
+    force two / three / four steps per pass on any lattice, "fuse0" single
+    steps only."""
+    if "fuse4" in tokens:
+        return "2", "4"
     if "fuse3" in tokens:
         return "2", "3"
     if "fuse2" in tokens:
@@ -102,8 +105,10 @@ def run_one(comm, name, steps, strict, face, out_dir, fuse="1", depth="2"):
     solver.advance(steps, store_moments_last=True)
     solver.plb.sync()
     finfo = solver.plb.fused_info()
-    pairs = finfo["pairs"] + finfo["triples"]
+    pairs = finfo["pairs"] + finfo["triples"] + finfo["quads"]
     if depth == "3" and finfo["n_deep3"] > 0 and steps > 3 and finfo["triples"] == 0:
+        pairs = 0
+    if depth == "4" and finfo["n_deep4"] > 0 and steps > 4 and finfo["quads"] == 0:
         pairs = 0
     got = solver.fields_to_host()
     shape = solver.state.domain.shape

@@ -33,12 +33,15 @@ SPECS = {
         "wide_cylinder:40:strict:p2p:fuse2",
         # three steps per pass: three list passes, three exchanges per pass
         "periodic_box:25:strict:p2p:fuse3", "cylinder_cut:26:strict:nccl:fuse3",
-        "wide_channel:41:strict:p2p:fuse3", "wide_cylinder:40:strict:nccl:fuse3"],
+        "wide_channel:41:strict:p2p:fuse3", "wide_cylinder:40:strict:nccl:fuse3",
+        "wide_channel:42:strict:p2p:fuse4", "wide_cylinder:41:strict:nccl:fuse4",
+        "periodic_box:25:strict:p2p:fuse4"],
     3: ["wide_cylinder:40:strict:p2p:fuse2", "poiseuille:25:strict:nccl:fuse2",
         "wide_channel:40:strict:p2p:fuse3"],
     4: ["uneven:41:strict:p2p:fuse2", "periodic_box:25:strict:p2p:fuse2",
         "wide_channel:60:strict:nccl:fuse2", "thin:60:strict:nccl",
-        "uneven:41:strict:p2p:fuse3", "wide_cylinder:61:strict:p2p:fuse3"],
+        "uneven:41:strict:p2p:fuse3", "wide_cylinder:61:strict:p2p:fuse3",
+        "wide_channel:61:strict:p2p:fuse4"],
 }
 
 

@@ -215,6 +215,29 @@ def test_three_steps_per_pass_equals_three_single_steps(emu, name):
             assert np.array_equal(got[key], want[key]), (name, rows, key)
 
 
+@pytest.mark.parametrize("name", sorted(WIDE_CASES))
+def test_four_steps_per_pass_equals_four_single_steps(emu, name):
+    """PLB_FUSE_DEPTH=4: one more level (58 of 64 nodes per warp strip, chunks
+    overlap by six rows, four list passes, three scratch lattices, deep flags
+    up to 3); 14 plain steps = 3 groups of four + 1 pair."""
+    factory = WIDE_CASES[name]
+    want, _ = _run(factory, 15, "0", emu)
+    for rows, one_by_one in ((None, False), (7, False), (64, True)):
+        got, info = _run(factory, 15, "2", emu, rows=rows, one_by_one=one_by_one,
+                         depth=4)
+        if info["n_deep4"] > 0:
+            assert info["active"] == 4 and info["quads"] == 3 and info["pairs"] == 1, info
+            assert info["n_deep4"] < info["n_deep3"] < info["n_deep"]
+        elif info["n_deep3"] > 0:
+            assert info["active"] == 3 and info["triples"] == 4 and info["pairs"] == 1, info
+        elif info["n_deep"] > 0:
+            assert info["active"] == 2 and info["pairs"] == 7, info
+        else:
+            assert info["active"] == 0
+        for key in ("density", "velocity", "pop_fluid_new"):
+            assert np.array_equal(got[key], want[key]), (name, rows, key)
+
+
 @pytest.mark.parametrize("name", sorted(cases.GOLDEN_CASES))
 def test_three_steps_per_pass_is_bit_exact_with_reference(golden_dir, emu, name):
     emu.setenv("PLB_FUSE", "2")

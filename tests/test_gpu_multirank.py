@@ -53,7 +53,10 @@ TWO_SLABS = ([f"{n}:25:strict:p2p" for n in NAMES] +
              # three steps per pass (PLB_FUSE_DEPTH=3, opt-in)
              ["periodic_box:25:strict:p2p:fuse3", "cylinder_cut:26:strict:nccl:fuse3",
               "wide_channel:41:strict:p2p:fuse3", "wide_cylinder:40:strict:nccl:fuse3",
-              "poiseuille:400:strict:p2p:fuse3"])
+              "poiseuille:400:strict:p2p:fuse3"] +
+             # four steps per pass
+             ["wide_channel:42:strict:p2p:fuse4", "wide_cylinder:41:strict:nccl:fuse4",
+              "poiseuille:401:strict:p2p:fuse4"])
 FOUR_SLABS = ([f"{n}:25:strict:p2p" for n in
                ("poiseuille", "cylinder_cut", "periodic_box")] +
               ["periodic_box:25:strict:nccl", "mrt_box:300:production:p2p",
@@ -62,7 +65,8 @@ FOUR_SLABS = ([f"{n}:25:strict:p2p" for n in
                "periodic_box:25:strict:p2p:fuse2",
                "wide_channel:60:strict:nccl:fuse2",
                "wide_cylinder:60:strict:p2p:fuse2",
-               "uneven:41:strict:p2p:fuse3", "wide_cylinder:61:strict:p2p:fuse3"])
+               "uneven:41:strict:p2p:fuse3", "wide_cylinder:61:strict:p2p:fuse3",
+               "wide_channel:61:strict:p2p:fuse4"])
 
 
 def _launch(world, specs, port):
