@@ -674,11 +674,14 @@ int step_fused(plb_solver *s, int depth)
 }
 
 // Steps per pass by default, per collision kernel (PLB_FUSE_DEPTH overrides).
-// Measured on the B200 (profiles/): the reference-ordered BGK kernels are
-// bound by the fp64 pipe at three steps per pass, a fourth only adds halo
-// work; the two-stress-moment MRT kernel is bound by HBM at three.
+// Measured on the B200 (profiles/r02_fused_sweep_v7_depth4.txt): the
+// two-stress-moment MRT kernel is bound by HBM at three steps per pass and
+// gains 14 % from a fourth (132.3 against 115.9 GLUPS; fp64 pipe 70 % busy
+// then); the reference-ordered BGK kernels are bound by the fp64 pipe at three
+// already (110.5 against 108.5), where a fourth costs a scratch lattice, a
+// list pass and a face exchange per group for 2 %.
 #ifndef PLB_FUSE_DEPTH_MRT
-#define PLB_FUSE_DEPTH_MRT 3
+#define PLB_FUSE_DEPTH_MRT 4
 #endif
 int default_fuse_depth(int kernel_collision)
 {

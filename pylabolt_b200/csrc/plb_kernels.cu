@@ -1493,7 +1493,7 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
 
 const char *kernel_build_info()
 {
-    static char text[320];
+    static char text[400];
     if (!text[0]) {
         const char *ring = PLB_FUSED_TENSOR       ? "tma-tensor"
                            : PLB_FUSED_BULK       ? "tma-bulk"
@@ -1501,13 +1501,14 @@ const char *kernel_build_info()
                                                   : "cp.async";
         snprintf(text, sizeof text,
                  "bulk: block=%d ld_mode=%d st_mode=%d; fused: block=%d "
-                 "ctas_per_sm=%d/%d/%d (mrt/bgk/depth3) stages=%d ring=%s carry=%s "
-                 "smem=%s (%d / %d bytes per cta at depth 2 / 3)%s",
+                 "ctas_per_sm=%d/%d/%d/%d (depth2/bgk3/mrt3/mrt4) stages=%d ring=%s carry=%s "
+                 "pin=%d smem=%s (%d / %d / %d bytes per cta at depth 2 / 3 / 4)%s",
                  PLB_BLOCK, PLB_LD_MODE, PLB_ST_MODE, PLB_FUSED_BLOCK,
-                 fused_min_blocks(2, 2), fused_min_blocks(0, 2), fused_min_blocks(2, 3),
+                 fused_min_blocks(2, 2), fused_min_blocks(0, 3), fused_min_blocks(2, 3),
+                 fused_min_blocks(2, 4),
                  PLB_FUSED_STAGES, ring, PLB_FUSED_CARRY_SMEM ? "shared" : "registers",
-                 PLB_FUSED_DYN_SMEM ? "dynamic" : "static", fused_smem_bytes(2),
-                 fused_smem_bytes(3),
+                 PLB_FUSED_PIN, PLB_FUSED_DYN_SMEM ? "dynamic" : "static", fused_smem_bytes(2),
+                 fused_smem_bytes(3), fused_smem_bytes(4),
 #ifdef PLB_EMU_RUNTIME
                  "; host emulation (test infrastructure)"
 #else

@@ -64,11 +64,13 @@ def test_own_arm_line():
         assert key in roof, key
     assert roof["bound"] == "hbm" and roof["unit"] == "GB/s"
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
-    # eleven steps = three three-step passes + one two-step pass, all counted
+    # eleven steps of the MRT channel = two four-step passes + one three-step
+    # pass, all counted
     reps = line["repeats"]
     assert reps >= 1 and len(line["repeat_ms"]) == reps
-    assert roof["triples"] == 3 * reps and roof["pairs"] == reps and roof["single_steps"] == 0
-    assert roof["steps_per_launch"] == 3 and line["config"]["steps_per_pass"] == 3
+    assert roof["quads"] == 2 * reps and roof["triples"] == reps
+    assert roof["pairs"] == 0 and roof["single_steps"] == 0
+    assert roof["steps_per_launch"] == 4 and line["config"]["steps_per_pass"] == 4
     assert roof["frac"] <= roof["step_equivalent_frac"]
     assert "fused: block=" in roof["kernel_build"]
     assert line["gpu_launches"] > 0

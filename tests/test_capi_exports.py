@@ -61,12 +61,13 @@ def test_product_never_imports_the_oracle():
 
 def test_build_info_describes_the_shipped_kernels():
     """plb_build_info needs no device: the shipped libraries are the measured
-    configuration (carry in shared memory, one-slot TMA ring, four / three
-    CTAs per SM for two / three steps per pass), production and strict alike."""
+    configuration (carry in shared memory, one-slot ring filled by one TMA
+    tensor copy per row, collision constants pinned, CTAs per SM per depth and
+    collision model), production and strict alike."""
     for strict in (False, True):
         text = capi.load_library(strict=strict).plb_build_info().decode()
-        assert "fused: block=128 ctas_per_sm=4/4/3" in text, text
-        assert "stages=1 ring=tma-bulk carry=shared smem=dynamic" in text, text
+        assert "fused: block=128 ctas_per_sm=4/4/3/3 (depth2/bgk3/mrt3/mrt4)" in text, text
+        assert "stages=1 ring=tma-tensor carry=shared pin=1 smem=dynamic" in text, text
         assert "emulation" not in text
 
 

@@ -299,8 +299,8 @@ def test_default_mode_pairs_only_where_deep_nodes_dominate(emu):
 
 
 def test_default_is_three_steps_per_pass(emu):
-    """Shipped default since round 2: plain steps go three at a time, a
-    remainder of two as a pair, a single one through the single-step kernel."""
+    """Shipped default for BGK: plain steps go three at a time, a remainder of
+    two as a pair, a single one through the single-step kernel."""
     emu.delenv("PLB_FUSE", raising=False)
     emu.delenv("PLB_FUSE_DEPTH", raising=False)
     factory = lambda: cases.cavity(201, 201)
@@ -312,6 +312,30 @@ def test_default_is_three_steps_per_pass(emu):
         s.plb.sync()
         info = s.plb.fused_info()
         assert info["triples"] == 3 and info["pairs"] == 1
+        s.advance(1, store_moments_last=True)
+        got = s.fields_to_host()
+    finally:
+        s.close()
+    want, _ = _run(factory, 12, "0", emu)
+    for key in ("density", "velocity", "pop_fluid_new"):
+        assert np.array_equal(got[key], want[key]), key
+
+
+def test_default_is_four_steps_per_pass_for_the_mrt_shortcut(emu):
+    """MRT with the reference's rates (the two-stress-moment kernel) groups
+    plain steps four at a time by default, a remainder of three as one
+    three-step pass."""
+    emu.delenv("PLB_FUSE", raising=False)
+    emu.delenv("PLB_FUSE_DEPTH", raising=False)
+    factory = lambda: _mrt(cases.poiseuille(210, 200))
+    s = make_solver(factory())
+    try:
+        info = s.plb.fused_info()
+        assert info["active"] == 4 and 0 < info["n_deep4"] < info["n_deep3"], info
+        s.advance(11)
+        s.plb.sync()
+        info = s.plb.fused_info()
+        assert info["quads"] == 2 and info["triples"] == 1 and info["pairs"] == 0, info
         s.advance(1, store_moments_last=True)
         got = s.fields_to_host()
     finally:

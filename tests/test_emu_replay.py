@@ -53,4 +53,4 @@ def test_smoke_entry_point_on_the_emulator():
          "import __graft_entry__ as g; g.smoke()"],
         capture_output=True, text=True, timeout=900, env=env, cwd=os.path.dirname(HERE))
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-3000:]
-    assert "three-step" in proc.stdout
+    assert "10 four-step" in proc.stdout

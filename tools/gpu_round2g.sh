@@ -20,10 +20,10 @@ timeout 300 python bench.py --impl reference --steps 20 --warmup 5 > $out/${tag}
 el reference-arm
 for wl in channel cavity; do
   timeout 240 ncu --set full --clock-control none --import-source on \
-      -k regex:k_bulk_fused -s 3 -c 1 -f -o $out/${tag}_ncu_${wl}_fused3 \
+      -k regex:k_bulk_fused -s 3 -c 1 -f -o $out/${tag}_ncu_${wl}_fused \
       python bench.py --workload $wl --steps 6 --warmup 6 --no-extras --no-cpu-baseline --no-parity > $out/${tag}_ncu_bench_$wl.log 2>&1
-  ncu -i $out/${tag}_ncu_${wl}_fused3.ncu-rep --page raw --csv > $out/${tag}_ncu_raw_${wl}_fused3.csv 2>/dev/null
-  ncu -i $out/${tag}_ncu_${wl}_fused3.ncu-rep --page details > $out/${tag}_ncu_details_${wl}_fused3.txt 2>/dev/null
+  ncu -i $out/${tag}_ncu_${wl}_fused.ncu-rep --page raw --csv > $out/${tag}_ncu_raw_${wl}_fused.csv 2>/dev/null
+  ncu -i $out/${tag}_ncu_${wl}_fused.ncu-rep --page details > $out/${tag}_ncu_details_${wl}_fused.txt 2>/dev/null
 done
 el ncu
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
