@@ -155,12 +155,12 @@ int plb_initialize_pop(plb_handle h);
 #define PLB_RECORD_LINKS 2
 int plb_step(plb_handle h, int64_t n_steps, int32_t flags);
 int plb_sync(plb_handle h);
-/* Several steps per pass.  Steps that need neither flag are advanced two at a
- * time where the geometry allows it: nodes whose whole neighbourhood is plain
- * fluid go through both steps in registers (lattice read once, written once:
- * 72 B per node and step instead of 144), all other nodes through two
- * ordinary passes hidden behind that kernel.  The result is the one of two
- * single steps (same per-node arithmetic).  Because plb_step() is
+/* Several steps per pass.  Steps that need neither flag are advanced several
+ * at a time where the geometry allows it: nodes whose whole neighbourhood is
+ * plain fluid go through all steps of a group on chip (lattice read once,
+ * written once: 144 / d B per node and step for d steps per pass), all other
+ * nodes through d ordinary passes hidden behind that kernel.  The result is
+ * the one of single steps (same per-node arithmetic).  Because plb_step() is
  * asynchronous, plain steps that do not fill a group may be held back until
  * the rest arrives; every other entry point first completes what was held
  * back.  Environment: PLB_FUSE=0 disables the path, PLB_FUSE=2 uses it on any
