@@ -21,7 +21,7 @@ el reference-arm
 for wl in channel cavity; do
   timeout 240 ncu --set full --clock-control none --import-source on \
       -k regex:k_bulk_fused -s 3 -c 1 -f -o $out/${tag}_ncu_${wl}_fused \
-      python bench.py --workload $wl --steps 6 --warmup 6 --no-extras --no-cpu-baseline --no-parity > $out/${tag}_ncu_bench_$wl.log 2>&1
+      python bench.py --workload $wl --steps 12 --warmup 12 --no-extras --no-cpu-baseline --no-parity > $out/${tag}_ncu_bench_$wl.log 2>&1
   ncu -i $out/${tag}_ncu_${wl}_fused.ncu-rep --page raw --csv > $out/${tag}_ncu_raw_${wl}_fused.csv 2>/dev/null
   ncu -i $out/${tag}_ncu_${wl}_fused.ncu-rep --page details > $out/${tag}_ncu_details_${wl}_fused.txt 2>/dev/null
 done

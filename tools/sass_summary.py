@@ -16,7 +16,8 @@ LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(
     REPO, "pylabolt_b200", "lib", "libplb.so")
 # (collision, forcing): 0/0 = BGK without forcing (cavity), 2/2 = two-stress-
 # moment MRT + Guo second order (channel)
-KERNELS = [r"k_bulk_fused<2, 2, 2>", r"k_bulk_fused<0, 0, 2>", r"k_bulk_fused<2, 2, 3>",
+KERNELS = [r"k_bulk_fused<2, 2, 4>", r"k_bulk_fused<0, 0, 3>", r"k_bulk_fused<2, 2, 3>",
+           r"k_bulk_fused<2, 2, 2>",
            r"k_bulk_vec2<2, 2, false>", r"k_bulk_vec2<0, 0, false>",
            r"k_links<2, 2, false>", r"k_face_unpack", r"k_face_signal"]
 GROUPS = [
@@ -25,6 +26,7 @@ GROUPS = [
     ("  of which 128-bit", r"^LDG\.E\.128|^LDG.*\.128"),
     ("async global->shared (LDGSTS)", r"^LDGSTS"),
     ("TMA bulk copies (UBLKCP)", r"^UBLKCP"),
+    ("TMA tensor copies (UTMALDG)", r"^UTMALDG"),
     ("shared loads (LDS)", r"^LDS"),
     ("global stores (STG)", r"^STG"),
     ("  of which 128-bit", r"^STG.*\.128"),
