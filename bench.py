@@ -593,6 +593,11 @@ def measure(workload, comm, rank, world, steps, warmup, scale, device,
                     ALGORITHMIC_BYTES_PER_NODE * dram_nodes / max(1, node_steps),
                 "step_equivalent_gbs": step_equiv,
                 "step_equivalent_frac": step_equiv / peak,
+                "frac_is": "144 B x the nodes one launch covers / launch time / peak: "
+                           "the bytes that must cross HBM.  The launch advances "
+                           "steps_per_launch steps on them; step_equivalent_frac "
+                           "(= frac x steps per launch) is the fraction of SURVEY's "
+                           "144 B per node and STEP roofline",
                 "fused": {k: finfo[k] for k in ("active", "n_deep", "n_deep3", "n_deep4",
                                                 "n_list1", "rows", "strips")},
                 "pairs": pairs, "triples": triples, "quads": quads,

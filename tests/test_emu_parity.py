@@ -238,10 +238,12 @@ def test_four_steps_per_pass_equals_four_single_steps(emu, name):
             assert np.array_equal(got[key], want[key]), (name, rows, key)
 
 
+@pytest.mark.parametrize("depth", [3, 4])
 @pytest.mark.parametrize("name", sorted(cases.GOLDEN_CASES))
-def test_three_steps_per_pass_is_bit_exact_with_reference(golden_dir, emu, name):
+def test_three_steps_per_pass_is_bit_exact_with_reference(golden_dir, emu, name, depth):
+    """The reference's own runs (golden vectors), three and four steps per pass."""
     emu.setenv("PLB_FUSE", "2")
-    emu.setenv("PLB_FUSE_DEPTH", "3")
+    emu.setenv("PLB_FUSE_DEPTH", str(depth))
     factory, kwargs, record = cases.GOLDEN_CASES[name]
     data = np.load(os.path.join(golden_dir, name + ".npz"))
     s = make_solver(factory(**kwargs))
@@ -254,7 +256,9 @@ def test_three_steps_per_pass_is_bit_exact_with_reference(golden_dir, emu, name)
             assert np.array_equal(got["density"], data[f"density_{step}"]), step
             assert np.array_equal(got["velocity"], data[f"velocity_{step}"]), step
             assert np.array_equal(got["pop_fluid_new"], data[f"pop_{step}"]), step
-        assert s.plb.fused_info()["triples"] > 0
+        info = s.plb.fused_info()
+        assert info["triples"] + info["quads"] > 0
+        assert info["active"] <= depth
     finally:
         s.close()
 
