@@ -725,7 +725,7 @@ int run_steps(plb_solver *s, int64_t n, int32_t flags)
 // plb_step() is asynchronous; with the fused path a single plain step is held
 // back until its partner arrives (or until any other entry point needs the
 // state), so that a host loop that issues one step per call -- the
-// reference's Solver.run -- still advances two steps per pass.
+// reference's Solver.run -- still advances several steps per pass.
 int flush_pending(plb_solver *s)
 {
     const int64_t n = s->pending;
@@ -1442,8 +1442,9 @@ int plb_finalize_geometry(plb_handle s)
                 // 32 rows beat 64 / 128 / 512 although 2 of 34 row loads are
                 // then redundant (more warps in their prologue at any time =
                 // more loads in flight); three steps per pass: 64 rows (4 of 68
-                // redundant) beat 32 and tie with 128.  Small lattices: >= 4
-                // waves of work items.
+                // redundant) beat 32 and tie with 128; four steps per pass: 64
+                // rows (132.3 GLUPS) against 127.4 / 131.3 / 132.1 / 130.7 with
+                // 32 / 48 / 96 / 128.  Small lattices: >= 4 waves of work items.
                 const int64_t want = nx * fused_strips(L, 2) / (148 * 16 * 4);
                 s->fused_rows[0] = int32_t(std::min<int64_t>(32, std::max<int64_t>(8, want)));
                 s->fused_rows[1] = int32_t(std::min<int64_t>(64, std::max<int64_t>(8, want)));

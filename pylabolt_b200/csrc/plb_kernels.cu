@@ -311,11 +311,11 @@ k_bulk_vec2(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
 }
 
 // ---------------------------------------------------------------------------
-// two time steps in one pass (temporal blocking in registers)
+// several time steps in one pass (temporal blocking on chip)
 // ---------------------------------------------------------------------------
 // The single-step kernels above move 144 B per node and step and run at the
 // HBM roofline; the only way past it is to touch HBM less.  k_bulk_fused
-// advances DEEP nodes by DEPTH = 2 (or 3) steps per pass: lattice A (time t)
+// advances DEEP nodes by DEPTH = 2, 3 or 4 steps per pass: lattice A (time t)
 // is read once, lattice B (time t + DEPTH) is written once, 144 / DEPTH bytes
 // per node and step.  The intermediate lattices never exist in memory:
 //
@@ -326,13 +326,13 @@ k_bulk_vec2(StepArgs a, int64_t x_begin, int32_t chunks_per_row)
 //   * the time-(t+1) state of the row before it is then complete in registers:
 //     k = 1, 5, 8 came from two rows back (two iterations old), k = 0, 2, 4
 //     from one row back (one iteration old), k = 3, 6, 7 are fresh.  It is
-//     collided again; with DEPTH = 3 the same hand-over happens once more, one
-//     row further back; the last collision is pushed into B exactly like
-//     k_bulk_vec2 pushes;
+//     collided again; with DEPTH = 3 (4) the same hand-over happens once
+//     (twice) more, one row further back each time; the last collision is
+//     pushed into B exactly like k_bulk_vec2 pushes;
 //   * every hand-over costs the strip its two outer nodes (no y-neighbour
-//     inside the warp), so a warp delivers 62 (60) of its 64 nodes and strips
-//     overlap by two (four); chunks of rows overlap by two (four) rows in x.
-//     The overlapped loads hit L2.  No block barrier anywhere.
+//     inside the warp), so a warp delivers 62 (60, 58) of its 64 nodes and
+//     strips overlap by two (four, six); chunks of rows overlap by two (four,
+//     six) rows in x.  The overlapped loads hit L2.  No block barrier anywhere.
 //
 // A node is deep enough for DEPTH steps if every node within Chebyshev
 // distance DEPTH - 1 is a bulk node (`deep` plane: that distance, capped).
@@ -348,16 +348,19 @@ __host__ __device__ constexpr int fused_span(int depth) { return 64 - 2 * (depth
 // Shipped configuration since round 2 (profiles/r02_fused_sweep_*.txt, 4096 x
 // 16384 sweep lattice, MRT + Guo / BGK):
 //   * the carried populations live in shared memory (PLB_FUSED_CARRY_SMEM), which
-//     takes three steps per pass from 200 to ~130 registers;
+//     takes three steps per pass from 200 to ~120 registers;
 //   * the row ring is ONE slot per warp filled by the TMA unit (PLB_FUSED_BULK,
-//     PLB_FUSED_STAGES = 1): refilled as soon as it has been read, it still
-//     fetches one row ahead, needs no destination registers and no LSU
-//     instruction in 31 of 32 lanes;
-//   * three 128-thread CTAs per SM for three steps per pass (55 KB of shared
-//     memory each), four for two steps per pass.
-// Three steps per pass: 109.0 / 96.3 GLUPS; the same with a cp.async ring of
-// two slots 103.9 / 92.4; carry in registers (200 registers, 8 warps) 88.6 /
-// 80.5; round 1's two-step kernel (registers, cp.async ring) 82.2 / 81.5.
+//     PLB_FUSED_STAGES = 1) with one tensor copy per row (PLB_FUSED_TENSOR):
+//     refilled as soon as it has been read, it still fetches one row ahead,
+//     needs no destination registers and no LSU instruction in 31 of 32 lanes;
+//   * CTAs of 128 threads; how many per SM is set by shared memory (37 / 55 /
+//     74 KB at two / three / four steps per pass) and, per collision model, by
+//     the register cap of fused_min_blocks().
+// History: round 1's two-step kernel (registers, cp.async ring) 82.2 / 81.5
+// GLUPS; three steps per pass with the carry in registers (200 registers, 8
+// warps) 88.6 / 80.5; carry in shared memory + nine bulk copies per row 109.0 /
+// 96.3; tensor copy + instruction diet 114.5 / 113.7; four steps per pass
+// 132.3 / 110.5 (the default for the two-stress-moment MRT kernel).
 #ifndef PLB_FUSED_MINBLOCKS
 #define PLB_FUSED_MINBLOCKS 4
 #endif
