@@ -717,6 +717,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
     typedef unsigned long long RingBars[PLB_FUSED_BLOCK / 32];
     RingBars *ring_bar = reinterpret_cast<RingBars *>(
         fused_smem + FUSED_RING_BYTES + LEVELS * FUSED_CARRY_LEVEL_BYTES);
+    (void)ring;
     (void)carry_s;
     (void)ring_bar;
 #else
@@ -1044,7 +1045,6 @@ __device__ __forceinline__ void node_velocity(const StepArgs &a, int64_t idx,
     const uint8_t c = a.code[idx];
     if (c == NODE_BULK || c == NODE_LINK) {
         double f[Q];
-#pragma unroll
         const int64_t off = lat_off(a.fin_map, idx);
 #pragma unroll
         for (int k = 0; k < Q; ++k) f[k] = a.fin[k * a.fin_plane + off];
