@@ -609,6 +609,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 #ifndef PLB_FUSED_PIN
 #define PLB_FUSED_PIN 1
 #endif
+// Neighbouring chunks march in opposite x directions (see k_bulk_fused);
+// PLB_FUSED_ALTERNATE in the environment overrides.
+#ifndef PLB_FUSED_ALTERNATE_DEFAULT
+#define PLB_FUSED_ALTERNATE_DEFAULT 1
+#endif
 __device__ __forceinline__ unsigned long long opaque_zero()
 {
 #ifdef PLB_EMU_RUNTIME
@@ -690,11 +695,48 @@ struct FusedCarry {
     double ca[3], cb[3];   // one row back : k = 0, 2, 4
 };
 
+// Hand-over between two levels with the carry in shared memory: stores what
+// this row has just produced for its successors and completes the row one
+// back, one step later.  DIR = +1: the warp marches towards larger x, so the
+// populations with c_x = +1 (1, 5, 8) were produced two iterations ago by the
+// row behind and those with c_x = -1 (3, 6, 7) are fresh from the row ahead;
+// DIR = -1 (march towards smaller x): the other way round.  c: this level's
+// nine slots (0-2 / 3-5: the behind-sourced populations of the even / odd
+// rows, 6-8: k = 0, 2, 4 of the previous row).
+template <int DIR>
+__device__ __forceinline__ void fused_hand_over(double2 (*c)[PLB_FUSED_BLOCK], int two_back,
+                                                const double sa[Q], const double sb[Q],
+                                                double fa[Q], double fb[Q])
+{
+    constexpr int B0 = DIR > 0 ? 1 : 3, B1 = DIR > 0 ? 5 : 6, B2 = DIR > 0 ? 8 : 7;
+    constexpr int A0 = DIR > 0 ? 3 : 1, A1 = DIR > 0 ? 6 : 5, A2 = DIR > 0 ? 7 : 8;
+    const int t = threadIdx.x;
+    const double2 p0 = c[two_back + 0][t];
+    const double2 p1 = c[two_back + 1][t];
+    const double2 p2 = c[two_back + 2][t];
+    const double2 c0 = c[6][t];
+    const double2 c2 = c[7][t];
+    const double2 c4 = c[8][t];
+    c[two_back + 0][t] = make_double2(sa[B0], sb[B0]);
+    c[two_back + 1][t] = make_double2(sa[B1], sb[B1]);
+    c[two_back + 2][t] = make_double2(sa[B2], sb[B2]);
+    c[6][t] = make_double2(sa[0], sb[0]);
+    c[7][t] = make_double2(sa[2], sb[2]);
+    c[8][t] = make_double2(sa[4], sb[4]);
+    fa[0] = c0.x; fa[2] = c2.x; fa[4] = c4.x;
+    fb[0] = c0.y; fb[2] = c2.y; fb[4] = c4.y;
+    fa[B0] = p0.x; fa[B1] = p1.x; fa[B2] = p2.x;
+    fb[B0] = p0.y; fb[B1] = p1.y; fb[B2] = p2.y;
+    fa[A0] = sa[A0]; fa[A1] = sa[A1]; fa[A2] = sa[A2];
+    fb[A0] = sb[A0]; fb[A1] = sb[A1]; fb[A2] = sb[A2];
+}
+
 template <int COLL, int FORCING, int DEPTH>
 __global__ void __launch_bounds__(PLB_FUSED_BLOCK, fused_min_blocks(COLL, DEPTH))
 k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
              int64_t x_end, int32_t strips, int32_t rows_per_chunk,
-             unsigned *work_counter, const PLB_GRID_CONSTANT TensorMap tmap)
+             unsigned *work_counter, const PLB_GRID_CONSTANT TensorMap tmap,
+             int32_t alternate)
 {
     constexpr int LEVELS = DEPTH - 1;              // hand-overs in registers
     const Layout &L = a.p.L;
@@ -793,15 +835,25 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         // number i = 0 ..); row number i leaves level l (0-based) as the complete
         // state of row i - 1 one step later, meaningful from i = 2 (l + 1) on; the
         // row pushed into B in iteration i is x = xs + i - 2 LEVELS.
+        // With `alternate`, odd chunks march the other way (row number i is
+        // x = xe - 1 + LEVELS - i): a chunk and its neighbour then reach the rows
+        // they share at the same time -- both at their start or both at their
+        // end -- and the second read of those 2 LEVELS rows is an L2 hit instead
+        // of a second trip to HBM (they were read ~100 us apart before, which
+        // no line survives at 5 TB/s).
         const int n_rows = int(xe - xs) + 2 * LEVELS;
-        const double *row0 = a.fin + L.at(xs - LEVELS, y);     // pair of row i = 0
+        const bool down = PLB_FUSED_CARRY_SMEM && alternate && (chunk & 1);
+        const int64_t x_first = down ? xe - 1 + LEVELS : xs - LEVELS;   // row number 0
+        const int64_t row_step = down ? -pitch : pitch;
+        const double *row0 = a.fin + L.at(x_first, y);          // pair of row i = 0
 #if PLB_FUSED_BULK
         constexpr int AHEAD = PLB_FUSED_STAGES;
 #if PLB_FUSED_TENSOR
         // the warp's box: 64 columns from the strip's first, row number j of the
         // item; a strip always begins inside the padded row
         const int box_col = int(L.y0 + y) - 2 * lane;
-        const int box_row0 = int(xs) - LEVELS + 1;
+        const int box_row0 = int(x_first) + 1;
+        const int box_step = down ? -1 : 1;
         constexpr unsigned run_bytes = 512;
         auto fill = [&](int j) {
             // cross-proxy fence + warp barrier: see the linear variant below
@@ -814,7 +866,8 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
                 const int slot = int(g % PLB_FUSED_STAGES);
                 unsigned long long *bar = &ring_bar[slot][wid];
                 mbar_expect_tx(bar, Q * run_bytes);
-                tensor_g2s(ring_row(slot, 0) - lane, &tmap, box_col, box_row0 + j, bar);
+                tensor_g2s(ring_row(slot, 0) - lane, &tmap, box_col, box_row0 + box_step * j,
+                           bar);
             }
         };
 #else
@@ -842,7 +895,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
 #pragma unroll
                 for (int k = 0; k < Q; ++k)
                     bulk_g2s(ring_row(int(g % PLB_FUSED_STAGES), k) - lane,
-                             run0 + k * plane + int64_t(j) * pitch, run_bytes, bar);
+                             run0 + k * plane + int64_t(j) * row_step, run_bytes, bar);
             }
         };
 #endif
@@ -855,7 +908,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
             if (in_row && i < n_rows) {
 #pragma unroll
                 for (int k = 0; k < Q; ++k)
-                    cp_async16(&ring[i][k][threadIdx.x], row0 + k * plane + i * pitch);
+                    cp_async16(&ring[i][k][threadIdx.x], row0 + k * plane + i * row_step);
             }
             cp_async_commit();
         }
@@ -874,13 +927,14 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         // deep flags of the row that is pushed in the NEXT iteration: fetched one
         // iteration ahead, so that the vote below never waits for them
         uint16_t dd_next = 0;
-        // node index of this lane's pair in the row pushed in iteration i
-        // (x = xs + i - 2 LEVELS), advanced by one row per iteration
-        int64_t idx = L.at(xs - 2 * LEVELS, y);
-        for (int i = 0; i < n_rows; ++i, idx += pitch) {
+        // node index of this lane's pair in the row pushed in iteration i (LEVELS
+        // rows behind the row loaded in that iteration), advanced by one row
+        // per iteration
+        int64_t idx = L.at(down ? x_first + LEVELS : x_first - LEVELS, y);
+        for (int i = 0; i < n_rows; ++i, idx += row_step) {
             const uint16_t dd = dd_next;
             if (in_row && i + 1 >= 2 * LEVELS && i + 1 < n_rows)
-                dd_next = *reinterpret_cast<const uint16_t *>(deep + idx + pitch);
+                dd_next = *reinterpret_cast<const uint16_t *>(deep + idx + row_step);
             double fa[Q], fb[Q];
 #if PLB_FUSED_BULK
             {
@@ -912,7 +966,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
 #pragma unroll
                     for (int k = 0; k < Q; ++k)
                         cp_async16(&ring[j % PLB_FUSED_STAGES][k][threadIdx.x],
-                                   row0 + k * plane + j * pitch);
+                                   row0 + k * plane + j * row_step);
                 }
                 cp_async_commit();
                 cp_async_wait<AHEAD>();                 // row i has landed
@@ -929,7 +983,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
 #pragma unroll
             for (int k = 0; k < Q; ++k) {
                 double2 v = make_double2(0.0, 0.0);
-                if (in_row) v = ld2(row0 + k * plane + i * pitch);
+                if (in_row) v = ld2(row0 + k * plane + i * row_step);
                 fa[k] = v.x;
                 fb[k] = v.y;
             }
@@ -947,25 +1001,9 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
 #endif
 #if PLB_FUSED_CARRY_SMEM
                 {
-                    double2(*c)[PLB_FUSED_BLOCK] = carry_s[l];
                     const int two_back = (i & 1) * 3;       // written two iterations ago
-                    const double2 p1 = c[two_back + 0][threadIdx.x];
-                    const double2 p5 = c[two_back + 1][threadIdx.x];
-                    const double2 p8 = c[two_back + 2][threadIdx.x];
-                    const double2 c0 = c[6][threadIdx.x];
-                    const double2 c2 = c[7][threadIdx.x];
-                    const double2 c4 = c[8][threadIdx.x];
-                    c[two_back + 0][threadIdx.x] = make_double2(sa[1], sb[1]);
-                    c[two_back + 1][threadIdx.x] = make_double2(sa[5], sb[5]);
-                    c[two_back + 2][threadIdx.x] = make_double2(sa[8], sb[8]);
-                    c[6][threadIdx.x] = make_double2(sa[0], sb[0]);
-                    c[7][threadIdx.x] = make_double2(sa[2], sb[2]);
-                    c[8][threadIdx.x] = make_double2(sa[4], sb[4]);
-                    // one step later: the populations of the row one back
-                    fa[0] = c0.x; fa[1] = p1.x; fa[2] = c2.x; fa[3] = sa[3]; fa[4] = c4.x;
-                    fa[5] = p5.x; fa[6] = sa[6]; fa[7] = sa[7]; fa[8] = p8.x;
-                    fb[0] = c0.y; fb[1] = p1.y; fb[2] = c2.y; fb[3] = sb[3]; fb[4] = c4.y;
-                    fb[5] = p5.y; fb[6] = sb[6]; fb[7] = sb[7]; fb[8] = p8.y;
+                    if (down) fused_hand_over<-1>(carry_s[l], two_back, sa, sb, fa, fb);
+                    else fused_hand_over<1>(carry_s[l], two_back, sa, sb, fa, fb);
                 }
 #else
                 FusedCarry &c = carry[l];
@@ -1450,7 +1488,7 @@ int fused_strips(const Layout &L, int depth)
 template <int C, int F, int D>
 static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
                       int64_t x_end, int32_t rows_per_chunk, unsigned *work_counter,
-                      const TensorMap &tmap, cudaStream_t st)
+                      const TensorMap &tmap, int32_t alternate, cudaStream_t st)
 {
     const int32_t strips = fused_strips(a.p.L, D);
     const int64_t chunks = (x_end - x_begin + rows_per_chunk - 1) / rows_per_chunk;
@@ -1491,7 +1529,7 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
     }
     PLB_LAUNCH_SMEM(COOP, (k_bulk_fused<C, F, D>), unsigned((warps + wpb - 1) / wpb),
                     PLB_FUSED_BLOCK, dyn_smem, st, a, deep, x_begin, x_end, strips,
-                    rows_per_chunk, work_counter, tmap);
+                    rows_per_chunk, work_counter, tmap, alternate);
 }
 
 const char *kernel_build_info()
@@ -1590,6 +1628,9 @@ int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
                       cudaStream_t stream)
 {
     if (x_end <= x_begin || depth < 2 || depth > 4) return 0;
+    // PLB_FUSED_ALTERNATE=0: every chunk marches towards larger x (A/B switch)
+    const char *alt_env = getenv("PLB_FUSED_ALTERNATE");
+    const int32_t alternate = alt_env ? atoi(alt_env) != 0 : PLB_FUSED_ALTERNATE_DEFAULT;
     static const TensorMap no_map = {};
     if (PLB_FUSED_TENSOR && !tmap_ptr) return 0;
     const TensorMap &tmap = tmap_ptr ? *tmap_ptr : no_map;
@@ -1597,13 +1638,13 @@ int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
     if (a.collision == C && a.forcing == F) {                                 \
         if (depth == 2)                                                       \
             run_fused<C, F, 2>(a, deep, x_begin, x_end, rows_per_chunk,       \
-                               work_counter, tmap, stream);                   \
+                               work_counter, tmap, alternate, stream);        \
         else if (depth == 3)                                                  \
             run_fused<C, F, 3>(a, deep, x_begin, x_end, rows_per_chunk,       \
-                               work_counter, tmap, stream);                   \
+                               work_counter, tmap, alternate, stream);        \
         else                                                                  \
             run_fused<C, F, 4>(a, deep, x_begin, x_end, rows_per_chunk,       \
-                               work_counter, tmap, stream);                   \
+                               work_counter, tmap, alternate, stream);        \
         return 1;                                                             \
     }
     PLB_CASE(0, 0) PLB_CASE(0, 1) PLB_CASE(0, 2)

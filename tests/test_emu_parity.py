@@ -302,6 +302,24 @@ def test_default_mode_pairs_only_where_deep_nodes_dominate(emu):
         large.close()
 
 
+@pytest.mark.parametrize("depth", [2, 3, 4])
+def test_chunks_marching_both_ways_equal_chunks_marching_one_way(emu, depth):
+    """Odd chunks march towards smaller x by default (their neighbours then
+    reach the shared halo rows at the same time); PLB_FUSED_ALTERNATE=0 sends
+    every chunk towards larger x.  Same fields, bit for bit, and equal to
+    single steps -- chunks of 3 rows: shorter than the halo at depth 4."""
+    factory = WIDE_CASES["mrt_poiseuille_70x140_guo2"]
+    want, _ = _run(factory, 13, "0", emu)
+    for alternate in ("1", "0"):
+        emu.setenv("PLB_FUSED_ALTERNATE", alternate)
+        for rows in (3, 8):
+            got, info = _run(factory, 13, "2", emu, rows=rows, depth=depth)
+            assert info["pairs"] + info["triples"] + info["quads"] > 0
+            for key in ("density", "velocity", "pop_fluid_new"):
+                assert np.array_equal(got[key], want[key]), (alternate, rows, key)
+    emu.delenv("PLB_FUSED_ALTERNATE", raising=False)
+
+
 def test_default_is_three_steps_per_pass(emu):
     """Shipped default for BGK: plain steps go three at a time, a remainder of
     two as a pair, a single one through the single-step kernel."""
