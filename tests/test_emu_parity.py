@@ -417,10 +417,8 @@ VARIANT_FLAGS = {
     "bulk_s3": ["-DPLB_FUSED_CARRY_SMEM=0", "-DPLB_FUSED_BULK=1", "-DPLB_FUSED_STAGES=3",
                 "-DPLB_FUSED_TENSOR=0"],
     # ... and PLB_FUSED_CARRY_SMEM=1: the carried populations in shared memory
-    # (everything in dynamic shared memory)
-    "carry_bulk_s3": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1",
-                      "-DPLB_FUSED_STAGES=3", "-DPLB_FUSED_TENSOR=0"],
-    # ... with a ring of one slot, refilled as soon as it has been read
+    # (everything in dynamic shared memory), a ring of one slot, refilled as
+    # soon as it has been read (round 2's first shipped configuration)
     "carry_bulk_s1": ["-DPLB_FUSED_CARRY_SMEM=1", "-DPLB_FUSED_BULK=1",
                       "-DPLB_FUSED_STAGES=1", "-DPLB_FUSED_TENSOR=0"],
     # PLB_FUSED_TENSOR=1 (the shipped default with one slot): a warp's row is one
