@@ -475,3 +475,48 @@ def test_uniform_initial_fields_are_filled_on_the_device(emu):
                                                 body.state.fields.velocity.nbytes)
     finally:
         body.close()
+
+
+def random_bodies_case(seed, nx=150, ny=200):
+    """Channel with pressure in / outlet and five circles / inclined ellipses
+    thrown in at random (non-overlapping, as the reference demands), some of
+    them closer to each other and to the walls than the radius a four-step
+    pass needs."""
+    rng = np.random.default_rng(seed)
+    sim = cases.cylinder(nx, ny, radius=6)
+    bodies = {"options": {}}
+    placed = []
+    for b in range(5):
+        for _ in range(50):
+            r = int(rng.integers(3, 9))
+            cx = int(rng.integers(r + 3, nx - r - 3))
+            cy = int(rng.integers(r + 3, ny - r - 3))
+            if all((cx - px) ** 2 + (cy - py) ** 2 > (r + pr + 2) ** 2
+                   for px, py, pr in placed):
+                placed.append((cx, cy, r))
+                break
+        else:
+            continue
+        if b % 2:
+            bodies[f"body{b}"] = {"type": "circle", "radius": r, "center": [cx, cy],
+                                  "density": 1.0, "static": True}
+        else:
+            bodies[f"body{b}"] = {"type": "ellipse", "semi_major_axis": float(r),
+                                  "semi_minor_axis": float(max(2, r - 2)),
+                                  "inclination_angle": float(rng.integers(0, 90)),
+                                  "center": [cx, cy], "density": 1.0, "static": True}
+    sim.obstacle_dict = bodies
+    return sim
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_bodies_every_depth_equals_single_steps(emu, seed):
+    """The deep flags, the list passes of every depth and the fused kernel
+    around randomly placed bodies must add up to single steps, bit for bit."""
+    factory = lambda: random_bodies_case(seed)
+    want, _ = _run(factory, 10, "0", emu)
+    for depth in (2, 3, 4):
+        got, info = _run(factory, 10, "2", emu, rows=9, depth=depth)
+        assert info["pairs"] + info["triples"] + info["quads"] > 0, info
+        for key in ("density", "velocity", "pop_fluid_new"):
+            assert np.array_equal(got[key], want[key]), (seed, depth, key)

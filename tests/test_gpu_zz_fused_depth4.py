@@ -6,7 +6,7 @@ scratch lattices).  Strict build, bit for bit against single steps.
 import numpy as np
 import pytest
 
-from test_emu_parity import WIDE_CASES
+from test_emu_parity import WIDE_CASES, random_bodies_case
 from test_gpu_fused import MID_CASES, _fields
 
 pytestmark = pytest.mark.gpu
@@ -44,3 +44,16 @@ def test_remainder_of_three_is_one_three_step_pass(monkeypatch):
     assert info["quads"] == 5 and info["triples"] == 1 and info["pairs"] == 0, info
     for key in ("density", "velocity", "pop_fluid_new"):
         assert np.array_equal(got[key], want[key]), key
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_bodies_every_depth_equals_single_steps(seed, monkeypatch):
+    """Randomly placed circles / ellipses in a 400 x 520 channel: deep flags,
+    list passes and the fused kernel of every depth add up to single steps."""
+    factory = lambda: random_bodies_case(seed, 400, 520)
+    want, _ = _fields(factory, 14, "0", True, monkeypatch)
+    for depth in (2, 3, 4):
+        got, info = _fields(factory, 14, "2", True, monkeypatch, depth=depth)
+        assert info["pairs"] + info["triples"] + info["quads"] > 0, info
+        for key in ("density", "velocity", "pop_fluid_new"):
+            assert np.array_equal(got[key], want[key]), (seed, depth, key)
