@@ -806,10 +806,31 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
             if (lane == 0) item = atomicAdd(work_counter, 1u);
             warp = __shfl_sync(0xffffffffu, item, 0);
         }
-        const int64_t chunk = warp / strips;
-        const int32_t strip = int32_t(warp - chunk * strips);
+        // item -> (chunk, strip): strips fastest, so that the warps of a CTA work
+        // on y-adjacent strips of one chunk; or (alternate & 2) the warps of a
+        // CTA take x-adjacent chunks of ONE strip, which -- marching in
+        // alternating directions, started together, equally long -- meet at
+        // every boundary between them at the same time
+        int64_t chunk = warp / strips;
+        int32_t strip = int32_t(warp - chunk * strips);
+        if (alternate & 2) {
+            constexpr int wpb = PLB_FUSED_BLOCK / 32;
+            const int64_t group = warp / wpb;
+            chunk = (group / strips) * wpb + (warp - group * wpb);
+            strip = int32_t(group % strips);
+        }
         const int64_t xs = x_begin + chunk * rows_per_chunk;
-        if (xs >= x_end) return;                       // whole warp
+        if (xs >= x_end) {                             // whole warp
+            // (with chunk groups an item past the last chunk may be followed by
+            // valid items of the next strip: a warp that draws its items from
+            // the queue goes on until the queue itself is exhausted)
+            const int64_t n_chunks = (x_end - x_begin + rows_per_chunk - 1) / rows_per_chunk;
+            constexpr int64_t wpb = PLB_FUSED_BLOCK / 32;
+            if (!work_counter || !(alternate & 2) ||
+                warp >= (n_chunks + wpb - 1) / wpb * wpb * strips)
+                return;
+            continue;
+        }
         const int64_t xe = (xs + rows_per_chunk < x_end) ? xs + rows_per_chunk : x_end;
         const int64_t y = int64_t(strip) * fused_span(DEPTH) - 2 + 2 * lane;
         // the pair lies inside the padded row (y >= -2 is column >= 14)
@@ -842,7 +863,7 @@ k_bulk_fused(StepArgs a, const uint8_t *__restrict__ deep, int64_t x_begin,
         // of a second trip to HBM (they were read ~100 us apart before, which
         // no line survives at 5 TB/s).
         const int n_rows = int(xe - xs) + 2 * LEVELS;
-        const bool down = PLB_FUSED_CARRY_SMEM && alternate && (chunk & 1);
+        const bool down = PLB_FUSED_CARRY_SMEM && (alternate & 1) && (chunk & 1);
         const int64_t x_first = down ? xe - 1 + LEVELS : xs - LEVELS;   // row number 0
         const int64_t row_step = down ? -pitch : pitch;
         const double *row0 = a.fin + L.at(x_first, y);          // pair of row i = 0
@@ -1492,8 +1513,10 @@ static void run_fused(const StepArgs &a, const uint8_t *deep, int64_t x_begin,
 {
     const int32_t strips = fused_strips(a.p.L, D);
     const int64_t chunks = (x_end - x_begin + rows_per_chunk - 1) / rows_per_chunk;
-    int64_t warps = chunks * strips;
     constexpr int wpb = PLB_FUSED_BLOCK / 32;
+    // (alternate & 2: a CTA takes wpb x-adjacent chunks of one strip; items
+    // beyond the last chunk return at once)
+    int64_t warps = (alternate & 2) ? (chunks + wpb - 1) / wpb * wpb * strips : chunks * strips;
     constexpr int dyn_smem = PLB_FUSED_DYN_SMEM ? fused_smem_bytes(D) : 0;
 #ifndef PLB_EMU_RUNTIME
     static bool attributes_set = false;
@@ -1629,8 +1652,10 @@ int launch_bulk_fused(const StepArgs &a, const uint8_t *deep, int depth,
 {
     if (x_end <= x_begin || depth < 2 || depth > 4) return 0;
     // PLB_FUSED_ALTERNATE=0: every chunk marches towards larger x (A/B switch)
+    // bit 0: odd chunks march towards smaller x; bit 1: the warps of a CTA take
+    // x-adjacent chunks of one strip instead of y-adjacent strips of one chunk
     const char *alt_env = getenv("PLB_FUSED_ALTERNATE");
-    const int32_t alternate = alt_env ? atoi(alt_env) != 0 : PLB_FUSED_ALTERNATE_DEFAULT;
+    const int32_t alternate = alt_env ? atoi(alt_env) & 3 : PLB_FUSED_ALTERNATE_DEFAULT;
     static const TensorMap no_map = {};
     if (PLB_FUSED_TENSOR && !tmap_ptr) return 0;
     const TensorMap &tmap = tmap_ptr ? *tmap_ptr : no_map;

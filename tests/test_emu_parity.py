@@ -310,10 +310,14 @@ def test_chunks_marching_both_ways_equal_chunks_marching_one_way(emu, depth):
     single steps -- chunks of 3 rows: shorter than the halo at depth 4."""
     factory = WIDE_CASES["mrt_poiseuille_70x140_guo2"]
     want, _ = _run(factory, 13, "0", emu)
-    for alternate in ("1", "0"):
+    # bit 0: odd chunks march towards smaller x; bit 1: the warps of a CTA take
+    # x-adjacent chunks of one strip (also with the work queue: items past the
+    # last chunk of a group are followed by valid ones)
+    for alternate in ("1", "0", "3", "2"):
         emu.setenv("PLB_FUSED_ALTERNATE", alternate)
         for rows in (3, 8):
-            got, info = _run(factory, 13, "2", emu, rows=rows, depth=depth)
+            got, info = _run(factory, 13, "2", emu, rows=rows, depth=depth,
+                             one_by_one=(alternate == "3" and rows == 8))
             assert info["pairs"] + info["triples"] + info["quads"] > 0
             for key in ("density", "velocity", "pop_fluid_new"):
                 assert np.array_equal(got[key], want[key]), (alternate, rows, key)
